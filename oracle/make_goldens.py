@@ -1,0 +1,145 @@
+"""Generate `tests/golden/*.npz` by executing the REFERENCE itself - TEST INFRASTRUCTURE.
+
+Run in the build container only (`python -m oracle.make_goldens`): imports
+`/root/reference/src/pipeedge` read-only, runs the reference's shard classes and quantisation
+functions on seeded synthetic inputs, and stores the outputs. `/root/reference` does not exist on
+the GPU box, so the fixtures (not this script) are what travels.
+
+Fixture contents
+----------------
+* `shards_<model>.npz` for the tiny test models: the complete value after EVERY sub-layer boundary
+  (tuples stored as `_0`/`_1`), the embeddings and the final logits, ubatch 2.
+* `shards_<registry model>.npz` for ViT-B, DeiT-B and BERT-base-CoLA at full size: logits plus a
+  strided sample of the hidden state after sub-layers 2, 24 and 48 (full tensors would be ~MBs).
+* `quant.npz`: `tensor_encode_outerdim` outputs and `tensor_decode_outerdim` round trips for
+  several bit widths, plus the two runtime hooks' clamp thresholds (restated in this script
+  without the `monitoring` calls - `runtime.py` itself cannot be imported here).
+"""
+import os
+import sys
+import numpy as np
+import torch
+
+REF_SRC = '/root/reference/src'
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, 'tests', 'golden')
+SAMPLE_STRIDE = 97   # prime, so the sample walks across rows and columns
+
+sys.path.insert(0, ROOT)
+from pipeedge_b200.synth import MODEL_SPECS, hf_config, synth_input, synth_weights  # noqa: E402
+
+
+def _ref():
+    sys.path.insert(0, REF_SRC)
+    # pylint: disable=import-outside-toplevel,import-error
+    from pipeedge.models import ModuleShardConfig
+    from pipeedge.models.transformers import bert, deit, vit
+    from pipeedge.quantization import basic_op, clamp_op
+    return ModuleShardConfig, {'vit': vit.ViTShardForImageClassification,
+                               'deit': deit.DeiTShardForImageClassification,
+                               'bert': bert.BertShardForSequenceClassification}, basic_op, clamp_op
+
+
+def ref_shard(spec, weights, layer_start, layer_end):
+    """Instantiate the reference shard class exactly as `model_cfg.module_shard_factory` does."""
+    shard_config_cls, classes, _, _ = _ref()
+    cfg = shard_config_cls(layer_start=layer_start, layer_end=layer_end,
+                           is_first=layer_start == 1, is_last=layer_end == spec.layers)
+    shard = classes[spec.family](hf_config(spec), cfg, weights)
+    shard.eval()   # deviation: the reference leaves BERT dropout live
+    return shard
+
+
+def _store(out, key, val):
+    if isinstance(val, tuple):
+        for i, t in enumerate(val):
+            out[f"{key}_{i}"] = t.numpy()
+    else:
+        out[key] = val.numpy()
+
+
+def golden_tiny(name, ubatch=2, seq_len=24):
+    spec = MODEL_SPECS[name]
+    weights = synth_weights(spec, seed=0)
+    x = synth_input(spec, ubatch, seed=1, seq_len=seq_len)
+    out = {'input': x.numpy()}
+    data = x
+    with torch.no_grad():
+        for layer in range(1, spec.layers + 1):
+            # one reference shard per sub-layer: its output IS the boundary payload
+            data = ref_shard(spec, weights, layer, layer)(data)
+            _store(out, f"after_{layer}", data)
+        out['logits_whole'] = ref_shard(spec, weights, 1, spec.layers)(x).numpy()
+    np.savez_compressed(os.path.join(OUT, f"shards_{name.replace('/', '_')}.npz"), **out)
+    print(name, 'done')
+
+
+def golden_full(name, ubatch, cuts, seq_len=128):
+    spec = MODEL_SPECS[name]
+    weights = synth_weights(spec, seed=0)
+    x = synth_input(spec, ubatch, seed=1, seq_len=seq_len)
+    out = {'ubatch': np.int64(ubatch), 'seq_len': np.int64(seq_len), 'cuts': np.array(cuts),
+           'stride': np.int64(SAMPLE_STRIDE)}
+    data = x
+    start = 1
+    with torch.no_grad():
+        for cut in cuts:
+            data = ref_shard(spec, weights, start, cut)(data)
+            start = cut + 1
+            if cut == spec.layers:
+                out['logits'] = data.numpy()
+            else:
+                out[f"after_{cut}_sample"] = data.numpy().reshape(-1)[::SAMPLE_STRIDE].copy()
+                out[f"after_{cut}_norm"] = np.float64(data.double().norm().item())
+    np.savez_compressed(os.path.join(OUT, f"shards_{name.replace('/', '_')}.npz"), **out)
+    print(name, 'done')
+
+
+def golden_quant():
+    _, _, basic_op, clamp_op = _ref()
+    out = {}
+    gen = torch.Generator().manual_seed(7)
+    shapes = {'a': (3, 17, 128), 'b': (2, 5, 77), 'c': (1, 33, 64)}
+    for tag, shape in shapes.items():
+        x = torch.randn(*shape, generator=gen) * 1.7 + 0.3
+        out[f"x_{tag}"] = x.numpy()
+        for bit in (2, 3, 4, 5, 6, 8, 10, 16):
+            # encode hook restated (runtime.py:83-86)
+            clamp = clamp_op.clamp_banner2019_laplace if x.min() < 0.2 else clamp_op.clamp_banner2019_gelu
+            xc = clamp(x, bit)
+            out[f"alpha_{tag}_{bit}"] = np.float32(xc.abs().max().item())   # == alpha when clamping bites
+            enc = basic_op.tensor_encode_outerdim(xc, bit)
+            for nm, t in zip(('comm', 'shape', 'scale', 'shift', 'bit'), enc):
+                out[f"{nm}_{tag}_{bit}"] = t.numpy()
+            out[f"dec_{tag}_{bit}"] = basic_op.tensor_decode_outerdim(enc).numpy()
+    # GeLU-clamp branch: all values >= 0.2
+    x = torch.rand(2, 9, 64, generator=gen) * 3 + 0.25
+    out['x_g'] = x.numpy()
+    for bit in (4, 8):
+        xc = clamp_op.clamp_banner2019_gelu(x, bit)
+        out[f"alpha_g_{bit}"] = np.float32(xc.abs().max().item())
+        enc = basic_op.tensor_encode_outerdim(xc, bit)
+        for nm, t in zip(('comm', 'shape', 'scale', 'shift', 'bit'), enc):
+            out[f"{nm}_g_{bit}"] = t.numpy()
+        out[f"dec_g_{bit}"] = basic_op.tensor_decode_outerdim(enc).numpy()
+    # bit 0 passthrough
+    enc = basic_op.tensor_encode_outerdim(x, 0)
+    for nm, t in zip(('comm', 'shape', 'scale', 'shift', 'bit'), enc):
+        out[f"{nm}_g_0"] = t.numpy()
+    np.savez_compressed(os.path.join(OUT, "quant.npz"), **out)
+    print('quant done')
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    golden_quant()
+    for name in ('test/vit-tiny', 'test/deit-tiny', 'test/bert-tiny'):
+        golden_tiny(name)
+    golden_full('google/vit-base-patch16-224', 2, (2, 24, 48))
+    golden_full('facebook/deit-base-distilled-patch16-224', 2, (6, 24, 48))
+    golden_full('textattack/bert-base-uncased-CoLA', 2, (6, 24, 48), seq_len=128)
+
+
+if __name__ == '__main__':
+    main()
