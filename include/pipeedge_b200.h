@@ -1,0 +1,190 @@
+/* pipeedge_b200 - C-ABI of the B200-native PipeEdge hot path.
+ *
+ * The reference (usc-isi/PipeEdge @ 1a68bbb) has no C/FFI boundary on this path: it sits behind three
+ * PYTHON contracts. This header is the boundary we define beneath them; each entry
+ * point names the reference interface it replaces. The Python classes in `pipeedge_b200/` (same names
+ * and signatures as the reference's) are the only callers; INTEGRATION.md shows the ctypes binding a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative PE_ERR_* code; `pe_last_error()` returns a
+ *    thread-local message for the last failure on the calling thread;
+ *  - all tensor arguments are DEVICE pointers owned by the caller, row-major, contiguous;
+ *    "f32" = IEEE binary32, "f16" = IEEE binary16, "u8" = bytes;
+ *  - `stream` is a `cudaStream_t` passed as `void*`; calls only enqueue work and never synchronise;
+ *  - no global mutable state besides per-handle state; callable with the Python GIL released;
+ *  - the library targets sm_100a only and refuses to run elsewhere (PE_ERR_DEVICE).
+ */
+#ifndef PIPEEDGE_B200_H
+#define PIPEEDGE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PE_OK 0
+#define PE_ERR_INVALID (-1) /* bad argument / unsupported shape */
+#define PE_ERR_CUDA (-2)    /* a CUDA runtime or driver call failed */
+#define PE_ERR_DEVICE (-3)  /* no sm_100 device */
+#define PE_ERR_NOMEM (-4)
+
+#define PE_ABI_VERSION 1
+
+/* Model family: selects pre-LN (ViT/DeiT: reference `vit.py:55-70`, `deit.py:54-69`) or post-LN
+ * (BERT: `bert.py:41-52`) block structure. */
+#define PE_FAMILY_VIT 0
+#define PE_FAMILY_DEIT 1
+#define PE_FAMILY_BERT 2
+
+/* Epilogues of pe_linear (what follows `A @ W^T + bias`). */
+#define PE_EPI_F16 0        /* out f16                                   (QKV projections)          */
+#define PE_EPI_GELU_F16 1   /* out f16 = gelu_erf(.)                     (ViTIntermediate/BertIntermediate) */
+#define PE_EPI_RESID_F32 2  /* out f32 = . + resid(f32)                  (ViTSelfOutput+skip, ViTOutput; BERT pre-LN sums) */
+#define PE_EPI_F32 3        /* out f32                                   (classifier heads)         */
+#define PE_EPI_TANH_F32 4   /* out f32 = tanh(.)                         (BertPooler)               */
+
+int pe_abi_version(void);
+const char* pe_last_error(void);
+/* Number of kernels this library has launched since load (all threads); bench.py reports it. */
+uint64_t pe_launch_count(void);
+
+/* ---- LayerNorm over the last dim -------------------------------------------------------------
+ * Replaces `nn.LayerNorm` at `vit.py:59,66,168`, the LayerNorm inside `BertSelfOutput`/`BertOutput`
+ * (HF modeling_bert.py:294-298,352-356) and `BertEmbeddings.LayerNorm`.
+ * x f32 [rows, hidden]; gamma/beta f32 [hidden]; writes out_f32 and/or out_f16 (either may be NULL).
+ * Statistics in fp32, two-pass (mean, then centred variance); eps added in fp32. */
+int pe_layernorm(const void* x, const void* gamma, const void* beta, float eps, void* out_f32, void* out_f16,
+                 int rows, int hidden, void* stream);
+
+/* ---- Dense contraction `out = epilogue(A @ W^T + bias)` on tcgen05 tensor cores ---------------
+ * Replaces every `nn.Linear` on the path (`ViTSelfAttention.query/key/value`, `ViTSelfOutput.dense`,
+ * `ViTIntermediate.dense`, `ViTOutput.dense` and the Bert equivalents; reference call sites
+ * `vit.py:60-69`, `bert.py:45-51`).
+ * a f16 [m, k]; w f16 [n, k] (the `nn.Linear.weight` layout); bias f32 [n] or NULL;
+ * resid f32 [m, n] (PE_EPI_RESID_F32 only; may alias `out`); out [m, n] f16 or f32 per epilogue.
+ * Requires k % 8 == 0 (16-byte TMA row pitch). fp32 accumulation in TMEM. */
+int pe_linear(const void* a, const void* w, const void* bias, const void* resid, void* out, int m, int n, int k,
+              int epilogue, void* stream);
+
+/* ---- Unmasked multi-head self-attention --------------------------------------------------------
+ * Replaces HF `eager_attention_forward` as invoked by `ViTSelfAttention`/`BertSelfAttention`
+ * (reference passes no mask: `vit.py:60`, `bert.py:45`): softmax(Q K^T * head_dim^-0.5) V.
+ * qkv f16 [batch*tokens, 3*heads*head_dim], columns = [Q | K | V], each head-major;
+ * ctx f16 [batch*tokens, heads*head_dim] (heads merged, as `context_layer.reshape`). head_dim == 64. */
+int pe_attention(const void* qkv, void* ctx, int batch, int tokens, int heads, int head_dim, void* stream);
+
+/* ---- f32 -> f16 cast (boundary payloads entering a mid-block stage) --------------------------- */
+int pe_cast_f32_to_f16(const void* src, void* dst, size_t n, void* stream);
+int pe_cast_f16_to_f32(const void* src, void* dst, size_t n, void* stream);
+
+/* ---- QuantPipe --------------------------------------------------------------------------------
+ * pe_quant_encode replaces `forward_hook_quant_encode` (`runtime.py:73-91`) for one tensor:
+ * optional Banner-2019 clamp (`clamp_op.py:11-33`; Laplace if min(x) < 0.2 else GeLU, threshold from
+ * the whole micro-batch) followed by `tensor_encode_outerdim` (`basic_op.py:114-170`): per item
+ * shift = min, scale = max - shift, code = rint((x - shift) / scale * (2^bit - 1)) in fp32 with IEEE
+ * sub/div/mul (no FMA contraction), packed LSB-first floor(32/bit) codes per little-endian uint32.
+ *   x      f32 [items, n]            codes  u8  [items, 4 * pe_quant_words(n, bit)]
+ *   scale  f32 [items]               shift  f32 [items]
+ *   alpha  f32 [1] (out, may be NULL): the clamp threshold used (+inf when clamp == 0)
+ *   work   scratch of at least pe_quant_workspace_bytes(items, n) bytes
+ * bit in [1,16]; clamp: 0 = none (bare tensor_encode_outerdim), 1 = runtime hook rule. */
+#define PE_CLAMP_NONE 0
+#define PE_CLAMP_AUTO 1
+#define PE_CLAMP_LAPLACE 2 /* force `clamp_banner2019_laplace` */
+#define PE_CLAMP_GELU 3    /* force `clamp_banner2019_gelu` */
+size_t pe_quant_words(size_t n, int bit);
+size_t pe_quant_workspace_bytes(int items, size_t n);
+int pe_quant_encode(const void* x, int items, size_t n, int bit, int clamp, void* codes, void* scale, void* shift,
+                    void* alpha, void* work, void* stream);
+/* Threshold only: the alpha that `clamp_banner2019_{laplace,gelu}(x, bit)` would clamp to
+ * (`clamp_op.py:11-33`), written to alpha f32 [1]; scale/shift f32 [items] receive the per-item
+ * parameters of the clamped tensor. Two kernels, no codes produced. */
+int pe_quant_alpha(const void* x, int items, size_t n, int bit, int clamp, void* scale, void* shift, void* alpha,
+                   void* work, void* stream);
+/* pe_quant_decode replaces `forward_pre_hook_quant_decode` / `tensor_decode_outerdim`
+ * (`runtime.py:93-119`, `basic_op.py:146-176`): out = f32(code / (2^bit - 1)) * scale + shift
+ * (float64 divide rounded to f32, then two fp32 roundings). out f32 [items, n]. */
+int pe_quant_decode(const void* codes, int items, size_t n, int bit, const void* scale, const void* shift, void* out,
+                    void* stream);
+/* The Lambert-W clamp factor `_clamp_factor_{laplace,gelu}` (`clamp_op.py:6-8,22-24`), as f32. */
+float pe_quant_clamp_factor(int bit, int gelu);
+
+/* ---- Stage executor ---------------------------------------------------------------------------
+ * Replaces `{ViT,DeiT,Bert}ModelShard.forward`'s loop over `{ViT,DeiT,Bert}LayerShard.forward`
+ * (`vit.py:161-170`, `deit.py:158-167`, `bert.py:142-151`) for the encoder blocks of one stage.
+ * Embeddings / final LayerNorm / pooler / classifier are separate calls (pe_* above) driven by the
+ * Python shard class. */
+typedef struct pe_block_weights {
+  /* f16 matrices in `nn.Linear.weight` layout [out, in]; f32 vectors. NULL for sub-layers this stage
+   * does not own. */
+  const void* w_qkv;  /* [3H, H] rows = [Wq; Wk; Wv] */
+  const void* b_qkv;  /* [3H] */
+  const void* w_o;    /* [H, H] */
+  const void* b_o;    /* [H] */
+  const void* w_fc1;  /* [I, H] */
+  const void* b_fc1;  /* [I] */
+  const void* w_fc2;  /* [H, I] */
+  const void* b_fc2;  /* [H] */
+  const void* ln1_w;  /* pre-LN: LayerNorm_before; post-LN: attention.output.LayerNorm */
+  const void* ln1_b;
+  const void* ln2_w;  /* pre-LN: LayerNorm_after;  post-LN: output.LayerNorm */
+  const void* ln2_b;
+} pe_block_weights;
+
+typedef struct pe_stage_desc {
+  int family;      /* PE_FAMILY_* */
+  int hidden;      /* H */
+  int heads;
+  int inter;       /* I */
+  int tokens;      /* S: tokens per item */
+  float eps;
+  int layer_start; /* 1-based inclusive sub-layer range, as `ModuleShardConfig` (`models/__init__.py:9-22`) */
+  int layer_end;
+  int max_ubatch;  /* workspace is sized for this many items */
+} pe_stage_desc;
+
+typedef struct pe_stage pe_stage;
+
+/* `blocks` has one entry per transformer block touched by [layer_start, layer_end], first to last. */
+int pe_stage_create(const pe_stage_desc* desc, const pe_block_weights* blocks, int n_blocks, pe_stage** out);
+int pe_stage_destroy(pe_stage* stage);
+/* Payloads follow SURVEY.md 8a-A2. in0/out0: f32 [ubatch, S, H] (or [ubatch, S, I] after sub-layer 2);
+ * in1/out1: the f32 skip tensor of a tuple payload, NULL otherwise. out0 may alias in0 only when the
+ * stage starts and ends on block boundaries. If `use_graph` != 0 the kernel sequence for this
+ * (ubatch, pointers) tuple is captured into a CUDA graph on first use and replayed afterwards. */
+int pe_stage_forward(pe_stage* stage, const void* in0, const void* in1, void* out0, void* out1, int ubatch,
+                     int use_graph, void* stream);
+/* Number of kernels one pe_stage_forward enqueues for `ubatch` items (for bench.py's gpu_launches). */
+int pe_stage_kernel_count(const pe_stage* stage);
+
+/* ---- Stage-0 edges ------------------------------------------------------------
+ * pe_patch_embed replaces HF `ViTEmbeddings` / `DeiTEmbeddings` as used at `vit.py:96,165`, `deit.py:95,161`:
+ * Conv2d(C, H, P, stride P) as an im2col + tcgen05 GEMM whose epilogue adds the conv bias and position
+ * rows and scatters into token rows n_prefix.. of each item; rows 0..n_prefix-1 are copied from `prefix`.
+ *   pixels f32 [B, C, img, img]; w f16 [H, kpad] (Conv2d weight flattened [H, C*P*P], zero-padded to
+ *   kpad = roundup(C*P*P, 8)); bias f32 [H]; pos f32 [S, H] with S = (img/P)^2 + n_prefix;
+ *   prefix f32 [n_prefix, H] = cls (and distillation) token + their position rows;
+ *   out f32 [B, S, H]; patches_work f16 [B * (img/P)^2, kpad] scratch. */
+int pe_patch_embed(const void* pixels, const void* w, const void* bias, const void* pos, const void* prefix, void* out,
+                   void* patches_work, int batch, int channels, int img, int patch, int hidden, int n_prefix,
+                   void* stream);
+/* pe_bert_embed replaces HF `BertEmbeddings` (eval mode) as used at `bert.py:78,146`:
+ * out = LayerNorm(word[ids] + type0 + pos[pos_ids[s]]).  ids i64 [B, S]; pos_ids i64 [S];
+ * word f32 [V, H]; type0 f32 [H] (token type 0 row); pos f32 [P, H]; out f32 [B, S, H]. */
+int pe_bert_embed(const void* ids, const void* pos_ids, const void* word, const void* type0, const void* pos,
+                  const void* gamma, const void* beta, float eps, void* out, int batch, int seq, int hidden,
+                  void* stream);
+
+/* ---- Debug / bring-up ------------------------------------------------------------------------
+ * Reference GEMM on CUDA cores (fp16 inputs, fp32 accumulate, same epilogues). Used ONLY by tests to
+ * localise a failure to the tcgen05 kernel; never selected by the product path. */
+int pe_debug_linear_simt(const void* a, const void* w, const void* bias, const void* resid, void* out, int m, int n,
+                         int k, int epilogue, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIPEEDGE_B200_H */

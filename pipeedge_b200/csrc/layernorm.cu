@@ -1,0 +1,125 @@
+// LayerNorm over the last dim (fp32 in, fp32 and/or fp16 out) and dtype casts. HBM/L2-bound:
+// one warp per row, 128-bit loads, the row lives in registers between the two statistics passes.
+// Replaces nn.LayerNorm at vit.py:59,66,168 and inside BertSelfOutput/BertOutput/BertEmbeddings.
+#include "../../include/pipeedge_b200.h"
+#include "common.cuh"
+
+namespace pe {
+
+void count_launches(int n);
+
+constexpr int kLnMaxVec = 12;  // float4 per lane: hidden <= 12 * 4 * 32 = 1536
+constexpr int kLnWarpsPerBlock = 4;
+
+__global__ void __launch_bounds__(kLnWarpsPerBlock * 32)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 float eps, float* out_f32, __half* out_f16, int rows, int hidden) {
+  const int row = blockIdx.x * kLnWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int nvec = hidden >> 2;  // hidden % 4 == 0 enforced by the host
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * hidden);
+  float4 v[kLnMaxVec];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nvec) {
+      v[i] = xr[idx];
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(sum) / static_cast<float>(hidden);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nvec) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float var = warp_sum(sq) / static_cast<float>(hidden);
+  const float rstd = 1.0f / sqrtf(var + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nvec) {
+      const float4 g = __ldg(g4 + idx), b = __ldg(b4 + idx);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + b.x;
+      o.y = (v[i].y - mean) * rstd * g.y + b.y;
+      o.z = (v[i].z - mean) * rstd * g.z + b.z;
+      o.w = (v[i].w - mean) * rstd * g.w + b.w;
+      if (out_f32 != nullptr) reinterpret_cast<float4*>(out_f32 + static_cast<size_t>(row) * hidden)[idx] = o;
+      if (out_f16 != nullptr) {
+        uint2 pk;
+        *reinterpret_cast<__half2*>(&pk.x) = __floats2half2_rn(o.x, o.y);
+        *reinterpret_cast<__half2*>(&pk.y) = __floats2half2_rn(o.z, o.w);
+        reinterpret_cast<uint2*>(out_f16 + static_cast<size_t>(row) * hidden)[idx] = pk;
+      }
+    }
+  }
+}
+
+int layernorm_impl(const void* x, const void* gamma, const void* beta, float eps, void* out_f32, void* out_f16,
+                   int rows, int hidden, cudaStream_t stream) {
+  PE_REQUIRE(x && gamma && beta && (out_f32 || out_f16), "pe_layernorm: null pointer");
+  PE_REQUIRE(rows > 0 && hidden > 0 && (hidden & 3) == 0 && hidden <= kLnMaxVec * 128,
+             "pe_layernorm: hidden=%d must be a multiple of 4 and <= %d", hidden, kLnMaxVec * 128);
+  const int grid = (rows + kLnWarpsPerBlock - 1) / kLnWarpsPerBlock;
+  layernorm_kernel<<<grid, kLnWarpsPerBlock * 32, 0, stream>>>(
+      static_cast<const float*>(x), static_cast<const float*>(gamma), static_cast<const float*>(beta), eps,
+      static_cast<float*>(out_f32), static_cast<__half*>(out_f16), rows, hidden);
+  PE_CUDA(cudaGetLastError());
+  count_launches(1);
+  return PE_OK;
+}
+
+__global__ void cast_f32_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t n4 = n >> 2;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    uint2 pk;
+    *reinterpret_cast<__half2*>(&pk.x) = __floats2half2_rn(v.x, v.y);
+    *reinterpret_cast<__half2*>(&pk.y) = __floats2half2_rn(v.z, v.w);
+    reinterpret_cast<uint2*>(dst)[i] = pk;
+  }
+  for (size_t i = (n4 << 2) + blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += stride)
+    dst[i] = __float2half_rn(src[i]);
+}
+
+__global__ void cast_f16_f32_kernel(const __half* __restrict__ src, float* __restrict__ dst, size_t n) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t n2 = n >> 1;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n2; i += stride) {
+    const float2 v = __half22float2(reinterpret_cast<const __half2*>(src)[i]);
+    reinterpret_cast<float2*>(dst)[i] = v;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) dst[n - 1] = __half2float(src[n - 1]);
+}
+
+int cast_impl(const void* src, void* dst, size_t n, bool to_half, cudaStream_t stream) {
+  PE_REQUIRE(src && dst, "pe_cast: null pointer");
+  if (n == 0) return PE_OK;
+  const int block = 256;
+  size_t want = (n / 4 + block - 1) / block;
+  const int grid = static_cast<int>(want < 1 ? 1 : (want > static_cast<size_t>(kNumSMs) * 8 ? kNumSMs * 8 : want));
+  if (to_half) {
+    PE_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0,
+               "pe_cast_f32_to_f16: misaligned");
+    cast_f32_f16_kernel<<<grid, block, 0, stream>>>(static_cast<const float*>(src), static_cast<__half*>(dst), n);
+  } else {
+    PE_REQUIRE((reinterpret_cast<uintptr_t>(src) & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0,
+               "pe_cast_f16_to_f32: misaligned");
+    cast_f16_f32_kernel<<<grid, block, 0, stream>>>(static_cast<const __half*>(src), static_cast<float*>(dst), n);
+  }
+  PE_CUDA(cudaGetLastError());
+  count_launches(1);
+  return PE_OK;
+}
+
+}  // namespace pe

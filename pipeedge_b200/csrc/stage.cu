@@ -1,0 +1,292 @@
+// Stage executor: runs the encoder-block sub-layers [layer_start, layer_end] of one pipeline stage as
+// a fixed sequence of the kernels in this library, optionally captured once into a CUDA graph and
+// replayed (the per-micro-batch sequence is launch-bound: ~7 kernels of a few microseconds per block).
+//
+// Data layout in HBM (per stage, sized for max_ubatch items of S tokens; M = ubatch * S rows):
+//   residual stream   f32 [M, H]   caller-owned (in0 / out0 / out1); updated in place after the first write
+//   a16               f16 [M, H]   LayerNorm output / f16 copy of the residual = A operand of QKV and FC1
+//   qkv16             f16 [M, 3H]  [Q | K | V], head-major inside each third
+//   ctx16             f16 [M, H]   merged-head attention context = A operand of the output projection
+//   inter16           f16 [M, I]   GELU(FC1) = A operand of FC2
+//   t32               f32 [M, H]   BERT only: pre-LayerNorm sum
+// Replaces {ViT,DeiT,Bert}ModelShard.forward's block loop (vit.py:161-170, deit.py:158-167, bert.py:142-151).
+#include <map>
+#include <tuple>
+#include <vector>
+
+#include "../../include/pipeedge_b200.h"
+#include "common.cuh"
+
+namespace pe {
+
+void count_launches(int n);
+int require_sm100();
+int linear_impl(const void* a, const void* w, const void* bias, const void* resid, void* out, int m, int n, int k,
+                int epilogue, int rows_per_item, int out_item_rows, int out_row_offset, int resid_per_item,
+                cudaStream_t stream);
+int layernorm_impl(const void* x, const void* gamma, const void* beta, float eps, void* out_f32, void* out_f16,
+                   int rows, int hidden, cudaStream_t stream);
+int attention_impl(const void* qkv, void* ctx, int batch, int tokens, int heads, int head_dim, cudaStream_t stream);
+int cast_impl(const void* src, void* dst, size_t n, bool to_half, cudaStream_t stream);
+
+struct SubRange {
+  int block;  // index into stage->blocks
+  int s0, s1; // sub-layers 0..3 inclusive
+};
+
+}  // namespace pe
+
+struct pe_stage {
+  pe_stage_desc d;
+  std::vector<pe_block_weights> blocks;
+  std::vector<pe::SubRange> ranges;
+  __half* a16 = nullptr;
+  __half* qkv16 = nullptr;
+  __half* ctx16 = nullptr;
+  __half* inter16 = nullptr;
+  float* t32 = nullptr;
+  int kernels_last = 0;
+  typedef std::tuple<int, const void*, const void*, void*, void*> Key;
+  struct Cached {
+    cudaGraphExec_t exec = nullptr;
+    bool warmed = false;
+  };
+  std::map<Key, Cached> graphs;
+};
+
+namespace pe {
+
+#define PE_TRY(call)              \
+  do {                            \
+    int _rc = (call);             \
+    if (_rc != PE_OK) return _rc; \
+  } while (0)
+
+static int lin(const void* a, const void* w, const void* b, const void* resid, void* out, int m, int n, int k, int epi,
+               cudaStream_t s) {
+  return linear_impl(a, w, b, resid, out, m, n, k, epi, 0, 0, 0, 0, s);
+}
+
+// Enqueue the kernel sequence of one forward on `stream`. Returns the number of kernels in *count.
+static int enqueue(pe_stage* st, const void* in0, const void* in1, void* out0, void* out1, int ubatch,
+                   cudaStream_t stream, int* count) {
+  const pe_stage_desc& d = st->d;
+  const int H = d.hidden, I = d.inter, S = d.tokens;
+  const int M = ubatch * S;
+  const bool post_ln = d.family == PE_FAMILY_BERT;
+  const int first_sub = st->ranges.front().s0, last_sub = st->ranges.back().s1;
+  const bool in_tuple = first_sub == 1 || first_sub == 3;
+  const bool out_tuple = last_sub == 0 || last_sub == 2;
+  PE_REQUIRE(in0 && out0, "pe_stage_forward: null payload");
+  PE_REQUIRE(!in_tuple || in1, "pe_stage_forward: stage starts mid-block and needs the (data, skip) tuple");
+  PE_REQUIRE(!out_tuple || out1, "pe_stage_forward: stage ends mid-block and produces a (data, skip) tuple");
+  int n_k = 0;
+
+  // every residual-stream write lands in the buffer that finally carries it out of the stage
+  float* resid_dest = static_cast<float*>(out_tuple ? out1 : out0);
+  const float* x = nullptr;     // current fp32 residual stream
+  const float* skip = nullptr;  // skip tensor of a pending (data, skip) tuple
+  bool a16_valid = false;       // a16 holds the f16 copy of x (post-LN only)
+
+  if (first_sub == 0 || first_sub == 2) {
+    x = static_cast<const float*>(in0);
+  } else if (first_sub == 1) {
+    PE_TRY(cast_impl(in0, st->ctx16, static_cast<size_t>(M) * H, true, stream)); ++n_k;
+    skip = static_cast<const float*>(in1);
+  } else {
+    PE_TRY(cast_impl(in0, st->inter16, static_cast<size_t>(M) * I, true, stream)); ++n_k;
+    skip = static_cast<const float*>(in1);
+  }
+
+  for (const SubRange& r : st->ranges) {
+    const pe_block_weights& w = st->blocks[r.block];
+    for (int sub = r.s0; sub <= r.s1; ++sub) {
+      switch (sub) {
+        case 0: {
+          if (post_ln) {
+            if (!a16_valid) { PE_TRY(cast_impl(x, st->a16, static_cast<size_t>(M) * H, true, stream)); ++n_k; }
+          } else {
+            PE_TRY(layernorm_impl(x, w.ln1_w, w.ln1_b, d.eps, nullptr, st->a16, M, H, stream)); ++n_k;
+          }
+          PE_TRY(lin(st->a16, w.w_qkv, w.b_qkv, nullptr, st->qkv16, M, 3 * H, H, PE_EPI_F16, stream)); ++n_k;
+          PE_TRY(attention_impl(st->qkv16, st->ctx16, ubatch, S, d.heads, H / d.heads, stream)); ++n_k;
+          skip = x; x = nullptr; a16_valid = false;
+          break;
+        }
+        case 1: {
+          if (post_ln) {
+            PE_TRY(lin(st->ctx16, w.w_o, w.b_o, skip, st->t32, M, H, H, PE_EPI_RESID_F32, stream)); ++n_k;
+            PE_TRY(layernorm_impl(st->t32, w.ln1_w, w.ln1_b, d.eps, resid_dest, st->a16, M, H, stream)); ++n_k;
+            a16_valid = true;
+          } else {
+            PE_TRY(lin(st->ctx16, w.w_o, w.b_o, skip, resid_dest, M, H, H, PE_EPI_RESID_F32, stream)); ++n_k;
+          }
+          x = resid_dest; skip = nullptr;
+          break;
+        }
+        case 2: {
+          if (post_ln) {
+            if (!a16_valid) { PE_TRY(cast_impl(x, st->a16, static_cast<size_t>(M) * H, true, stream)); ++n_k; }
+          } else {
+            PE_TRY(layernorm_impl(x, w.ln2_w, w.ln2_b, d.eps, nullptr, st->a16, M, H, stream)); ++n_k;
+          }
+          PE_TRY(lin(st->a16, w.w_fc1, w.b_fc1, nullptr, st->inter16, M, I, H, PE_EPI_GELU_F16, stream)); ++n_k;
+          skip = x; x = nullptr; a16_valid = false;
+          break;
+        }
+        default: {
+          if (post_ln) {
+            PE_TRY(lin(st->inter16, w.w_fc2, w.b_fc2, skip, st->t32, M, H, I, PE_EPI_RESID_F32, stream)); ++n_k;
+            PE_TRY(layernorm_impl(st->t32, w.ln2_w, w.ln2_b, d.eps, resid_dest, st->a16, M, H, stream)); ++n_k;
+            a16_valid = true;
+          } else {
+            PE_TRY(lin(st->inter16, w.w_fc2, w.b_fc2, skip, resid_dest, M, H, I, PE_EPI_RESID_F32, stream)); ++n_k;
+          }
+          x = resid_dest; skip = nullptr;
+          break;
+        }
+      }
+    }
+  }
+
+  if (out_tuple) {
+    // (ctx | inter, skip): the f16 operand is widened for the fp32 wire format of the boundary payload
+    if (last_sub == 0) { PE_TRY(cast_impl(st->ctx16, out0, static_cast<size_t>(M) * H, false, stream)); ++n_k; }
+    else { PE_TRY(cast_impl(st->inter16, out0, static_cast<size_t>(M) * I, false, stream)); ++n_k; }
+    if (skip != static_cast<const float*>(out1)) {
+      PE_CUDA(cudaMemcpyAsync(out1, skip, static_cast<size_t>(M) * H * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    }
+  }
+  *count = n_k;
+  return PE_OK;
+}
+
+static int build_ranges(pe_stage* st) {
+  // same walk as ViTModelShard._build_shard (vit.py:99-113): 1-based sub-layer l -> block ceil(l/4)-1
+  const int ls = st->d.layer_start, le = st->d.layer_end;
+  const int first_block = (ls + 3) / 4 - 1, last_block = (le + 3) / 4 - 1;
+  int cur = ls;
+  while (cur <= le) {
+    const int block = (cur + 3) / 4 - 1;
+    const int s0 = (cur - 1) % 4;
+    const int s1 = block == last_block ? (le - 1) % 4 : 3;
+    st->ranges.push_back({block - first_block, s0, s1});
+    cur += s1 - s0 + 1;
+  }
+  return last_block - first_block + 1;
+}
+
+}  // namespace pe
+
+extern "C" {
+
+int pe_stage_create(const pe_stage_desc* desc, const pe_block_weights* blocks, int n_blocks, pe_stage** out) {
+  using namespace pe;
+  PE_REQUIRE(desc && blocks && out, "pe_stage_create: null pointer");
+  PE_REQUIRE(desc->family >= PE_FAMILY_VIT && desc->family <= PE_FAMILY_BERT, "pe_stage_create: bad family %d",
+             desc->family);
+  PE_REQUIRE(desc->layer_start >= 1 && desc->layer_end >= desc->layer_start, "pe_stage_create: bad layer range [%d,%d]",
+             desc->layer_start, desc->layer_end);
+  PE_REQUIRE(desc->hidden > 0 && desc->heads > 0 && desc->hidden % desc->heads == 0 && desc->hidden / desc->heads == 64,
+             "pe_stage_create: hidden=%d heads=%d (head_dim must be 64)", desc->hidden, desc->heads);
+  PE_REQUIRE(desc->hidden % 8 == 0 && desc->inter % 8 == 0 && desc->inter > 0, "pe_stage_create: bad hidden/inter");
+  PE_REQUIRE(desc->tokens > 0 && desc->max_ubatch > 0, "pe_stage_create: bad tokens/max_ubatch");
+  int rc = require_sm100();
+  if (rc != PE_OK) return rc;
+  pe_stage* st = new pe_stage();
+  st->d = *desc;
+  const int need = build_ranges(st);
+  if (need != n_blocks) {
+    set_error("pe_stage_create: layers [%d,%d] touch %d blocks but %d weight sets were given", desc->layer_start,
+              desc->layer_end, need, n_blocks);
+    delete st;
+    return PE_ERR_INVALID;
+  }
+  st->blocks.assign(blocks, blocks + n_blocks);
+  for (const SubRange& r : st->ranges) {
+    const pe_block_weights& w = st->blocks[r.block];
+    bool ok = true;
+    for (int s = r.s0; s <= r.s1; ++s) {
+      if (s == 0) ok = ok && w.w_qkv && w.b_qkv && (desc->family == PE_FAMILY_BERT || (w.ln1_w && w.ln1_b));
+      if (s == 1) ok = ok && w.w_o && w.b_o && (desc->family != PE_FAMILY_BERT || (w.ln1_w && w.ln1_b));
+      if (s == 2) ok = ok && w.w_fc1 && w.b_fc1 && (desc->family == PE_FAMILY_BERT || (w.ln2_w && w.ln2_b));
+      if (s == 3) ok = ok && w.w_fc2 && w.b_fc2 && (desc->family != PE_FAMILY_BERT || (w.ln2_w && w.ln2_b));
+    }
+    if (!ok) {
+      set_error("pe_stage_create: missing weights for block %d sub-layers %d-%d", r.block, r.s0, r.s1);
+      delete st;
+      return PE_ERR_INVALID;
+    }
+  }
+  const size_t M = static_cast<size_t>(desc->max_ubatch) * desc->tokens;
+  const size_t H = desc->hidden, I = desc->inter;
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = cudaMalloc(&st->a16, M * H * sizeof(__half));
+  if (e == cudaSuccess) e = cudaMalloc(&st->qkv16, M * 3 * H * sizeof(__half));
+  if (e == cudaSuccess) e = cudaMalloc(&st->ctx16, M * H * sizeof(__half));
+  if (e == cudaSuccess) e = cudaMalloc(&st->inter16, M * I * sizeof(__half));
+  if (e == cudaSuccess) e = cudaMalloc(&st->t32, M * H * sizeof(float));
+  if (e != cudaSuccess) {
+    set_error("pe_stage_create: workspace allocation failed: %s", cudaGetErrorString(e));
+    pe_stage_destroy(st);
+    return PE_ERR_NOMEM;
+  }
+  *out = st;
+  return PE_OK;
+}
+
+int pe_stage_destroy(pe_stage* st) {
+  if (st == nullptr) return PE_OK;
+  for (auto& kv : st->graphs)
+    if (kv.second.exec != nullptr) cudaGraphExecDestroy(kv.second.exec);
+  cudaFree(st->a16);
+  cudaFree(st->qkv16);
+  cudaFree(st->ctx16);
+  cudaFree(st->inter16);
+  cudaFree(st->t32);
+  delete st;
+  return PE_OK;
+}
+
+int pe_stage_forward(pe_stage* st, const void* in0, const void* in1, void* out0, void* out1, int ubatch, int use_graph,
+                     void* stream_v) {
+  using namespace pe;
+  PE_REQUIRE(st != nullptr, "pe_stage_forward: null stage");
+  PE_REQUIRE(ubatch > 0 && ubatch <= st->d.max_ubatch, "pe_stage_forward: ubatch=%d outside [1,%d]", ubatch,
+             st->d.max_ubatch);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!use_graph) return enqueue(st, in0, in1, out0, out1, ubatch, stream, &st->kernels_last);
+
+  pe_stage::Cached& c = st->graphs[pe_stage::Key(ubatch, in0, in1, out0, out1)];
+  if (c.exec != nullptr) {
+    PE_CUDA(cudaGraphLaunch(c.exec, stream));
+    count_launches(st->kernels_last);
+    return PE_OK;
+  }
+  if (!c.warmed) {
+    // first use: run eagerly (one-time cudaFuncSetAttribute / driver entry-point lookups happen here)
+    c.warmed = true;
+    return enqueue(st, in0, in1, out0, out1, ubatch, stream, &st->kernels_last);
+  }
+  // second use: capture the same sequence, instantiate, launch
+  cudaGraph_t graph = nullptr;
+  PE_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+  int n_k = 0;
+  const int rc = enqueue(st, in0, in1, out0, out1, ubatch, stream, &n_k);
+  const cudaError_t end = cudaStreamEndCapture(stream, &graph);
+  if (rc != PE_OK) {
+    if (graph != nullptr) cudaGraphDestroy(graph);
+    return rc;
+  }
+  PE_CUDA(end);
+  const cudaError_t inst = cudaGraphInstantiate(&c.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  PE_CUDA(inst);
+  st->kernels_last = n_k;
+  PE_CUDA(cudaGraphLaunch(c.exec, stream));
+  return PE_OK;  // kernels were already counted by enqueue() during capture
+}
+
+int pe_stage_kernel_count(const pe_stage* st) { return st == nullptr ? 0 : st->kernels_last; }
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+"""GPU: each kernel of libpipeedge_b200.so, called through the C-ABI, against a plain fp32 restatement.
+
+LayerNorm / GEMM / attention are floating point: compared with torch fp32 maths on the same (fp16-rounded)
+operands, tolerances written in each test. The tcgen05 GEMM is additionally compared with the library's own
+CUDA-core debug GEMM to localise failures.
+"""
+import math
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from pipeedge_b200 import ops as _ops
+    return _ops
+
+
+def _lib():
+    from pipeedge_b200 import _lib
+    return _lib
+
+
+@pytest.mark.parametrize('rows,hidden', [(394, 768), (197, 1024), (34, 128), (7, 192), (64, 1280), (1, 384)])
+def test_layernorm(ops, rows, hidden):
+    gen = torch.Generator().manual_seed(rows * 31 + hidden)
+    x = (torch.randn(rows, hidden, generator=gen) * 2.0 + 0.5)
+    g = 1 + 0.1 * torch.randn(hidden, generator=gen)
+    b = 0.1 * torch.randn(hidden, generator=gen)
+    want = F.layer_norm(x, (hidden,), g, b, 1e-12)
+    o32, o16 = ops.layernorm(x.cuda(), g.cuda(), b.cuda(), 1e-12, want_f32=True, want_f16=True)
+    torch.testing.assert_close(o32.cpu(), want, rtol=2e-5, atol=2e-5)
+    torch.testing.assert_close(o16.cpu().float(), want, rtol=1e-3, atol=1e-3)   # one fp16 rounding
+
+
+def _gemm_case(m, n, k, seed):
+    gen = torch.Generator().manual_seed(seed)
+    a = torch.randn(m, k, generator=gen).half()
+    w = (torch.randn(n, k, generator=gen) * 0.05).half()
+    bias = torch.randn(n, generator=gen)
+    resid = torch.randn(m, n, generator=gen)
+    return a, w, bias, resid
+
+
+def _gemm_ref(a, w, bias, resid, epi):
+    lib = _lib()
+    acc = a.double() @ w.double().t() + bias.double()
+    if epi == lib.PE_EPI_GELU_F16:
+        acc = F.gelu(acc)
+    elif epi == lib.PE_EPI_TANH_F32:
+        acc = torch.tanh(acc)
+    elif epi == lib.PE_EPI_RESID_F32:
+        acc = acc + resid.double()
+    return acc.float()
+
+
+GEMM_SHAPES = [(128, 256, 64), (128, 128, 128), (256, 512, 768), (1576, 2304, 768), (1576, 768, 3072),
+               (197, 3072, 768), (200, 1000, 768), (2, 2, 768), (300, 776, 136), (4096, 768, 768), (33, 40, 72)]
+
+
+@pytest.mark.parametrize('epi_name', ['PE_EPI_F16', 'PE_EPI_GELU_F16', 'PE_EPI_RESID_F32', 'PE_EPI_F32', 'PE_EPI_TANH_F32'])
+def test_linear_simt_debug_kernel(ops, epi_name):
+    """The CUDA-core debug GEMM itself is right (it is the comparator for the tcgen05 kernel)."""
+    epi = getattr(_lib(), epi_name)
+    a, w, bias, resid = _gemm_case(77, 200, 136, 5)
+    want = _gemm_ref(a, w, bias, resid, epi)
+    got = ops.linear(a.cuda(), w.cuda(), bias.cuda(), epi, resid=resid.cuda(), debug_simt=True)
+    tol = 2e-3 if 'F16' in epi_name else 2e-5
+    torch.testing.assert_close(got.cpu().float(), want, rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize('m,n,k', GEMM_SHAPES)
+def test_linear_tcgen05_f32(ops, m, n, k):
+    """fp32-out epilogue: only accumulation order differs from the fp64 reference -> tight tolerance."""
+    lib = _lib()
+    a, w, bias, resid = _gemm_case(m, n, k, m + n + k)
+    want = _gemm_ref(a, w, bias, resid, lib.PE_EPI_F32)
+    got = ops.linear(a.cuda(), w.cuda(), bias.cuda(), lib.PE_EPI_F32)
+    torch.cuda.synchronize()
+    scale = want.abs().max().item()
+    err = (got.cpu() - want).abs().max().item()
+    assert err <= 2e-5 * max(1.0, scale) * math.sqrt(k / 64), f"max abs err {err} (scale {scale})"
+
+
+@pytest.mark.parametrize('epi_name', ['PE_EPI_F16', 'PE_EPI_GELU_F16', 'PE_EPI_RESID_F32', 'PE_EPI_TANH_F32'])
+@pytest.mark.parametrize('m,n,k', [(1576, 768, 768), (394, 3072, 768), (200, 1000, 136)])
+def test_linear_tcgen05_epilogues(ops, epi_name, m, n, k):
+    epi = getattr(_lib(), epi_name)
+    a, w, bias, resid = _gemm_case(m, n, k, 11 + m)
+    want = _gemm_ref(a, w, bias, resid, epi)
+    got = ops.linear(a.cuda(), w.cuda(), bias.cuda(), epi, resid=resid.cuda())
+    simt = ops.linear(a.cuda(), w.cuda(), bias.cuda(), epi, resid=resid.cuda(), debug_simt=True)
+    tol = 2e-3 if 'F16' in epi_name else 5e-5
+    torch.testing.assert_close(got.cpu().float(), want, rtol=tol, atol=tol)
+    torch.testing.assert_close(got.cpu().float(), simt.cpu().float(), rtol=tol, atol=tol)
+
+
+def test_linear_resid_in_place(ops):
+    """`out` may alias `resid` (the residual stream is updated in place inside a stage)."""
+    lib = _lib()
+    a, w, bias, resid = _gemm_case(500, 768, 768, 3)
+    want = _gemm_ref(a, w, bias, resid, lib.PE_EPI_RESID_F32)
+    buf = resid.cuda().clone()
+    ops.linear(a.cuda(), w.cuda(), bias.cuda(), lib.PE_EPI_RESID_F32, resid=buf, out=buf)
+    torch.testing.assert_close(buf.cpu(), want, rtol=5e-5, atol=5e-5)
+
+
+def test_linear_rejects_bad_arguments(ops):
+    lib = _lib()
+    a, w, bias, _ = _gemm_case(16, 16, 12, 1)     # k % 8 != 0
+    with pytest.raises(lib.PipeEdgeB200Error):
+        ops.linear(a.cuda(), w.cuda(), bias.cuda(), lib.PE_EPI_F32)
+    with pytest.raises(ValueError):
+        ops.linear(a, w, bias, lib.PE_EPI_F32)    # CPU tensors: there is no CPU path
+
+
+@pytest.mark.parametrize('batch,tokens,heads', [(2, 197, 12), (1, 128, 2), (3, 17, 2), (1, 64, 1), (1, 65, 1),
+                                                (2, 198, 12), (1, 1, 1), (1, 512, 2)])
+def test_attention(ops, batch, tokens, heads):
+    gen = torch.Generator().manual_seed(tokens + heads)
+    hidden = heads * 64
+    qkv = (torch.randn(batch * tokens, 3 * hidden, generator=gen) * 1.5).half()
+    q, k, v = [t.float().view(batch, tokens, heads, 64).transpose(1, 2) for t in qkv.split(hidden, dim=1)]
+    probs = F.softmax(torch.matmul(q, k.transpose(2, 3)) * 0.125, dim=-1)
+    want = torch.matmul(probs, v).transpose(1, 2).reshape(batch * tokens, hidden)
+    got = ops.attention(qkv.cuda(), batch, tokens, heads)
+    # P is rounded to fp16 before P.V and the output is fp16: 2e-3 absolute on O(1) values
+    torch.testing.assert_close(got.cpu().float(), want, rtol=2e-3, atol=2e-3)
