@@ -1,0 +1,531 @@
+"""Peer-to-peer pipeline communication - drop-in for `pipeedge.comm.p2p` (reference `p2p/__init__.py`).
+
+Same classes and call contract (`DistP2pContext`, `DistP2pPipelineStage` with `enqueue_tensor`, the four
+`register_*_hook`s, `work_cb` / `results_cb`, FIFO per hop, back-pressure through size-1 queues), rebuilt
+for one rank per B200:
+
+* The DEVICE of a tensor picks its plane. CUDA tensors (activations, int8 codes, per-item scales) travel
+  over a dedicated 2-rank NCCL communicator per hop direction on a side stream, ordered against the compute
+  stream with CUDA events, so the hop of micro-batch i overlaps the compute of micro-batch i+1 without the
+  host ever waiting on the GPU. CPU tensors and the (cached) payload header travel over Gloo, as every
+  message does in the reference (`p2p/__init__.py:96-121`).
+* One NCCL communicator per ordered rank pair: the reference's send and receive threads run concurrently
+  (`p2p/__init__.py:155-258`) and NCCL serialises a communicator's operations on one internal stream, so a
+  shared communicator could deadlock when two ranks send to each other (stage 0 <-> last stage on 2 ranks).
+* The command channel (`cmd_broadcast`, `CommandThread`; `p2p/__init__.py:75-85,298-331`) stays on Gloo:
+  NCCL has neither tags nor any-source receive.
+
+Without CUDA (the CPU test-suite) everything rides Gloo and the classes behave like the reference's.
+"""
+import collections
+import pickle
+import queue
+import threading
+import time
+from typing import Any, Callable, List, Optional, Tuple
+import torch
+import torch.distributed as dist
+from .. import DistCmdHandler, DistContext
+
+# Gloo message tags
+TAG_CMD = 10          # [cmd, n_tensors]
+TAG_CMD_META = 11     # per command tensor: [n_bytes] then pickled (dtype, shape)
+TAG_CMD_DATA = 12
+TAG_DATA_HDR = 0      # [header_bytes]; 0 = same header as the previous payload on this hop
+TAG_DATA_META = 1     # pickled payload description
+TAG_DATA_CPU = 2      # CPU tensors of the payload, in order
+
+_POLL_SEC = 0.0002
+_RECV_SLOTS = 4       # ring of device receive buffers per payload position
+
+
+class ConditionQueue(queue.Queue):
+    """A Queue with a public `condition: threading.Condition` for synchronization (`p2p/__init__.py:88-93`)."""
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        self.condition = threading.Condition()
+
+
+class _Payload:
+    """What the internal queues carry: the user-visible data plus device-side ordering information."""
+    __slots__ = ('data', 'ready', 'on_consumed')
+
+    def __init__(self, data: Any, ready: Optional['torch.cuda.Event'] = None,
+                 on_consumed: Optional[Callable[['torch.cuda.Event'], None]] = None):
+        self.data = data                # Tensor | Tuple[Tensor | object, ...]
+        self.ready = ready              # recorded when the producing stream has written `data`
+        self.on_consumed = on_consumed  # given an event recorded after the consumer's reads
+
+
+def _cuda_tensors(data) -> List[torch.Tensor]:
+    objs = data if isinstance(data, tuple) else (data,)
+    return [o for o in objs if isinstance(o, torch.Tensor) and o.is_cuda]
+
+
+class DistP2pContext(DistContext):
+    """The singleton distributed P2P context manager (`p2p/__init__.py:41-85`).
+
+    Parameters are the reference's: `ipg_args` / `ipg_kwargs` for `torch.distributed.init_process_group()`
+    (the default group is the Gloo control plane) and the command handler `cmd_cb`. When CUDA is available, one
+    NCCL process group per ordered rank pair is created for the data plane.
+    """
+    _instance: Optional['DistP2pContext'] = None
+
+    def __init__(self, ipg_args: tuple, ipg_kwargs: dict, cmd_cb: DistCmdHandler):
+        super().__init__(ipg_args, ipg_kwargs)
+        self._thread_cmd = CommandThread(cmd_cb)
+        self._hop_groups = {}
+
+    def init(self) -> None:
+        """Initialize the distributed context and threads."""
+        super().init()
+        dist.init_process_group(*self._init_args, **self._init_kwargs)
+        if torch.cuda.is_available() and self._world_size > 1:
+            # every rank must create every group, in the same order
+            for src in range(self._world_size):
+                for dst in range(self._world_size):
+                    if src != dst:
+                        self._hop_groups[(src, dst)] = dist.new_group(ranks=[src, dst], backend='nccl')
+        DistP2pContext._instance = self
+        self._thread_cmd.start()
+
+    def shutdown(self) -> None:
+        """Shutdown threads and the distributed context."""
+        super().shutdown()
+        self._thread_cmd.stop()
+        self._thread_cmd.join()
+        DistP2pContext._instance = None
+        dist.destroy_process_group()
+
+    @classmethod
+    def hop_group(cls, src: int, dst: int):
+        """NCCL group for the directed hop `src -> dst` (None when the data plane is Gloo)."""
+        inst = cls._instance
+        return None if inst is None else inst._hop_groups.get((src, dst))   # pylint: disable=protected-access
+
+    def cmd_broadcast(self, cmd: int, tensors: Optional[Tuple[torch.Tensor, ...]] = None) -> None:
+        """Broadcast a command with optional (CPU) tensors to every other rank (`p2p/__init__.py:72-85`)."""
+        assert self._initialized
+        tensors = () if tensors is None else tuple(tensors)
+        head = torch.tensor([cmd, len(tensors)], dtype=torch.int)
+        reqs = []
+        keep = []
+        for dst in range(self._world_size):
+            if dst == self._rank:
+                continue
+            reqs.append(dist.isend(head, dst=dst, tag=TAG_CMD))
+            for tensor in tensors:
+                tensor = tensor.detach().cpu().contiguous()
+                meta = torch.frombuffer(bytearray(pickle.dumps((tensor.dtype, tuple(tensor.shape)))), dtype=torch.uint8)
+                size = torch.tensor([meta.numel()], dtype=torch.int64)
+                keep += [meta, size, tensor]
+                reqs.append(dist.isend(size, dst=dst, tag=TAG_CMD_META))
+                reqs.append(dist.isend(meta, dst=dst, tag=TAG_CMD_META))
+                if tensor.numel() > 0:
+                    reqs.append(dist.isend(tensor.view(-1), dst=dst, tag=TAG_CMD_DATA))
+        for req in reqs:
+            req.wait()
+
+
+def _poll(req, stop_evt: threading.Event) -> bool:
+    """Wait for a distributed request, giving up (False) when `stop_evt` is set."""
+    while not req.is_completed():
+        if stop_evt.is_set():
+            return False
+        time.sleep(_POLL_SEC)
+    return True
+
+
+class AbstractTensorExchangeThread(threading.Thread):
+    """Abstract tensor exchange thread with pre/post hooks (`p2p/__init__.py:124-152`)."""
+
+    def __init__(self):
+        super().__init__(daemon=True)
+        self._pre_hooks = []
+        self._post_hooks = []
+        self._evt_stop_thread = threading.Event()
+        self._device = torch.cuda.current_device() if torch.cuda.is_available() else None
+        self._stream = None
+
+    def register_pre_hook(self, hook: Callable[..., None], args: tuple) -> None:
+        """Register hook with signature: `hook(*args)`."""
+        self._pre_hooks.append((hook, args))
+
+    def register_post_hook(self, hook: Callable[..., None], args: tuple) -> None:
+        """Register hook with signature: `hook(tensors, *args)`."""
+        self._post_hooks.append((hook, args))
+
+    def _call_pre_hooks(self):
+        for hook, args in self._pre_hooks:
+            hook(*args)
+
+    def _call_post_hooks(self, tensors):
+        for hook, args in self._post_hooks:
+            hook(tensors, *args)
+
+    def _enter_device(self):
+        if self._device is not None:
+            torch.cuda.set_device(self._device)
+            self._stream = torch.cuda.Stream(device=self._device)
+
+
+def _describe(objs: tuple, is_tuple: bool):
+    """Picklable description of a payload + the CPU tensors and CUDA tensors to ship."""
+    items, cpu, cuda = [], [], []
+    for obj in objs:
+        if isinstance(obj, torch.Tensor):
+            plane = 'cuda' if obj.is_cuda else 'cpu'
+            items.append((plane, obj.dtype, tuple(obj.shape)))
+            (cuda if obj.is_cuda else cpu).append(obj)
+        else:
+            items.append(('obj', pickle.dumps(obj), None))   # non-tensor objects ride in the header (util.py:28-38)
+    return {'tuple': is_tuple, 'items': items}, cpu, cuda
+
+
+class TensorSendThread(AbstractTensorExchangeThread):
+    """Thread for sending payloads to `dst_rank` (`p2p/__init__.py:155-204`)."""
+
+    def __init__(self, queue_out: ConditionQueue, dst_rank: int):
+        super().__init__()
+        self._queue_out = queue_out
+        self._dst_rank = dst_rank
+        self._last_meta = None
+        self._inflight = collections.deque()
+
+    def stop(self) -> None:
+        """Direct the thread to stop."""
+        with self._queue_out.condition:
+            self._evt_stop_thread.set()
+            self._queue_out.condition.notify_all()
+
+    def run(self):
+        """Dequeue payloads and send them."""
+        self._enter_device()
+        group = DistP2pContext.hop_group(dist.get_rank(), self._dst_rank)
+        while not self._evt_stop_thread.is_set():
+            with self._queue_out.condition:
+                while self._queue_out.empty():
+                    if self._evt_stop_thread.is_set():
+                        return
+                    self._queue_out.condition.wait()
+                payload = self._queue_out.get(block=False)
+                self._queue_out.condition.notify_all()
+            data = payload.data
+            is_tuple = isinstance(data, tuple)
+            objs = data if is_tuple else (data,)
+            desc, cpu, cuda = _describe(objs, is_tuple)
+            meta = pickle.dumps(desc)
+            # header: only re-sent when the payload's structure changes (shapes are static per schedule)
+            if meta == self._last_meta:
+                dist.send(torch.zeros(1, dtype=torch.int64), dst=self._dst_rank, tag=TAG_DATA_HDR)
+            else:
+                buf = torch.frombuffer(bytearray(meta), dtype=torch.uint8)
+                dist.send(torch.tensor([buf.numel()], dtype=torch.int64), dst=self._dst_rank, tag=TAG_DATA_HDR)
+                dist.send(buf, dst=self._dst_rank, tag=TAG_DATA_META)
+                self._last_meta = meta
+            self._call_pre_hooks()
+            for tensor in cpu:
+                if tensor.numel() > 0:
+                    dist.send(tensor.contiguous().view(-1), dst=self._dst_rank, tag=TAG_DATA_CPU)
+            if cuda:
+                if group is None:
+                    raise RuntimeError("CUDA tensors in a payload need the NCCL data plane (DistP2pContext with CUDA)")
+                with torch.cuda.stream(self._stream):
+                    if payload.ready is not None:
+                        self._stream.wait_event(payload.ready)
+                    ops = []
+                    for tensor in cuda:
+                        tensor.record_stream(self._stream)
+                        ops.append(dist.P2POp(dist.isend, tensor.contiguous(), self._dst_rank, group=group))
+                    for work in dist.batch_isend_irecv(ops):   # one ncclGroup -> one kernel for the whole payload
+                        work.wait()                            # stream-level wait only: the host does not block
+                    done = torch.cuda.Event()
+                    done.record(self._stream)
+                if payload.on_consumed is not None:
+                    payload.on_consumed(done)
+                # bound the number of sends the host may run ahead of the device
+                self._inflight.append(done)
+                while len(self._inflight) > 2:
+                    self._inflight.popleft().synchronize()
+            elif payload.on_consumed is not None:
+                payload.on_consumed(None)
+            self._call_post_hooks(tuple(t for t in objs if isinstance(t, torch.Tensor)))
+
+
+class TensorRecvThread(AbstractTensorExchangeThread):
+    """Thread for receiving payloads from `src_rank` (`p2p/__init__.py:207-258`)."""
+
+    def __init__(self, queue_in: ConditionQueue, src_rank: int):
+        super().__init__()
+        self._queue_in = queue_in
+        self._src_rank = src_rank
+        self._desc = None
+        self._rings = {}
+        self._count = 0
+
+    def stop(self) -> None:
+        """Direct the thread to stop."""
+        self._evt_stop_thread.set()
+
+    def _slot(self, pos: int, dtype, shape):
+        """Next device receive buffer for payload position `pos`, plus its 'consumer finished' guard."""
+        key = (pos, dtype, shape)
+        ring = self._rings.get(key)
+        if ring is None:
+            ring = [[torch.empty(shape, dtype=dtype, device=torch.device('cuda', self._device)), None]
+                    for _ in range(_RECV_SLOTS)]
+            self._rings[key] = ring
+        return ring[self._count % _RECV_SLOTS]
+
+    def run(self):
+        """Receive payloads and enqueue them."""
+        self._enter_device()
+        group = DistP2pContext.hop_group(self._src_rank, dist.get_rank())
+        while True:
+            hdr = torch.zeros(1, dtype=torch.int64)
+            if not _poll(dist.irecv(hdr, src=self._src_rank, tag=TAG_DATA_HDR), self._evt_stop_thread):
+                return
+            if int(hdr[0]) > 0:
+                buf = torch.empty(int(hdr[0]), dtype=torch.uint8)
+                dist.recv(buf, src=self._src_rank, tag=TAG_DATA_META)
+                self._desc = pickle.loads(buf.numpy().tobytes())
+            desc = self._desc
+            self._call_pre_hooks()
+            objs: List[Any] = []
+            cuda_slots = []
+            for pos, (plane, dtype, shape) in enumerate(desc['items']):
+                if plane == 'obj':
+                    objs.append(pickle.loads(dtype))
+                elif plane == 'cpu':
+                    tensor = torch.empty(shape, dtype=dtype)
+                    if tensor.numel() > 0:
+                        dist.recv(tensor.view(-1), src=self._src_rank, tag=TAG_DATA_CPU)
+                    objs.append(tensor)
+                else:
+                    slot = self._slot(pos, dtype, shape)
+                    cuda_slots.append(slot)
+                    objs.append(slot[0])
+            ready = None
+            on_consumed = None
+            if cuda_slots:
+                with torch.cuda.stream(self._stream):
+                    ops = []
+                    for slot in cuda_slots:
+                        if slot[1] is not None:
+                            self._stream.wait_event(slot[1])    # the previous consumer of this buffer is done
+                        ops.append(dist.P2POp(dist.irecv, slot[0], self._src_rank, group=group))
+                    for work in dist.batch_isend_irecv(ops):
+                        work.wait()
+                    ready = torch.cuda.Event()
+                    ready.record(self._stream)
+
+                def on_consumed(evt, slots=tuple(cuda_slots)):
+                    for slot in slots:
+                        slot[1] = evt
+            self._count += 1
+            self._call_post_hooks(tuple(t for t in objs if isinstance(t, torch.Tensor)))
+            data = tuple(objs) if desc['tuple'] else objs[0]
+            with self._queue_in.condition:
+                while self._queue_in.full():
+                    if self._evt_stop_thread.is_set():
+                        return
+                    self._queue_in.condition.wait(0.05)
+                self._queue_in.put(_Payload(data, ready, on_consumed))
+                self._queue_in.condition.notify_all()
+
+
+class TensorWorkThread(threading.Thread):
+    """Thread for processing payloads with `callback` (`p2p/__init__.py:261-295`)."""
+
+    def __init__(self, queue_in: ConditionQueue, queue_out: Optional[ConditionQueue], callback: Callable):
+        super().__init__(daemon=True)
+        self._queue_in = queue_in
+        self._queue_out = queue_out
+        self._callback = callback
+        self._evt_stop_thread = threading.Event()
+        self._device = torch.cuda.current_device() if torch.cuda.is_available() else None
+        self.exception: Optional[BaseException] = None
+
+    def stop(self) -> None:
+        """Direct the thread to stop."""
+        with self._queue_in.condition:
+            self._evt_stop_thread.set()
+            self._queue_in.condition.notify_all()
+
+    def run(self):
+        """Dequeue, process, enqueue."""
+        stream = None
+        if self._device is not None:
+            torch.cuda.set_device(self._device)
+            stream = torch.cuda.Stream(device=self._device)
+        while True:
+            with self._queue_in.condition:
+                while self._queue_in.empty():
+                    if self._evt_stop_thread.is_set():
+                        return
+                    self._queue_in.condition.wait()
+                payload = self._queue_in.get(block=False)
+                self._queue_in.condition.notify_all()
+            try:
+                if stream is not None:
+                    with torch.cuda.stream(stream):
+                        if payload.ready is not None:
+                            stream.wait_event(payload.ready)
+                        result = self._callback(payload.data)
+                        done = torch.cuda.Event()
+                        done.record(stream)
+                    if payload.on_consumed is not None:
+                        payload.on_consumed(done)
+                else:
+                    result = self._callback(payload.data)
+                    done = None
+                    if payload.on_consumed is not None:
+                        payload.on_consumed(None)
+            except BaseException as exc:   # pylint: disable=broad-except
+                # the reference loses worker exceptions and hangs; keep it for the owner to re-raise
+                self.exception = exc
+                raise
+            if result is not None and self._queue_out is not None:
+                with self._queue_out.condition:
+                    while self._queue_out.full():
+                        if self._evt_stop_thread.is_set():
+                            return
+                        self._queue_out.condition.wait(0.05)
+                    self._queue_out.put(_Payload(result, done))
+                    self._queue_out.condition.notify_all()
+
+
+class CommandThread(threading.Thread):
+    """Thread for receiving commands from any rank (`p2p/__init__.py:298-331`)."""
+
+    def __init__(self, callback: DistCmdHandler):
+        super().__init__(daemon=True)
+        self._callback = callback
+        self._evt_stop_thread = threading.Event()
+
+    def stop(self) -> None:
+        """Direct the thread to stop."""
+        self._evt_stop_thread.set()
+
+    def run(self):
+        """Listen for commands."""
+        while True:
+            head = torch.zeros(2, dtype=torch.int)
+            req = dist.irecv(head, tag=TAG_CMD)
+            while not req.is_completed():
+                if self._evt_stop_thread.is_set():
+                    return
+                time.sleep(0.01)
+            src = req.source_rank() if hasattr(req, 'source_rank') else None
+            cmd, count = int(head[0]), int(head[1])
+            tensors = ()
+            for _ in range(count):
+                size = torch.zeros(1, dtype=torch.int64)
+                dist.recv(size, src=src, tag=TAG_CMD_META)
+                meta = torch.empty(int(size[0]), dtype=torch.uint8)
+                dist.recv(meta, src=src, tag=TAG_CMD_META)
+                dtype, shape = pickle.loads(meta.numpy().tobytes())
+                tensor = torch.empty(shape, dtype=dtype)
+                if tensor.numel() > 0:
+                    dist.recv(tensor.view(-1), src=src, tag=TAG_CMD_DATA)
+                tensors += (tensor,)
+            self._callback(cmd, tensors)
+
+
+class DistP2pPipelineStage:
+    """The singleton distributed P2P pipeline stage context manager (`p2p/__init__.py:334-450`).
+
+    `rank_src` / `rank_dst`: ranks to receive payloads from / send them to (None = not applicable);
+    `work_cb(payload) -> payload | None`: the stage's shard (None relays); `results_cb(payload)`: consumer of
+    the last stage's output on the data rank. Thread and queue topology follow the reference's `_create_stage`.
+    """
+
+    def __init__(self, rank_src: Optional[int], rank_dst: Optional[int], work_cb: Optional[Callable],
+                 results_cb: Optional[Callable[[Any], None]]):
+        self._initialized = False
+        self._queues = {}
+        self._threads = {}
+        self._create_stage(rank_src, rank_dst, work_cb, results_cb)
+
+    def _create_stage(self, rank_src, rank_dst, work_cb, results_cb):
+        self._queues['in'] = ConditionQueue(maxsize=1)
+        self._queues['out'] = ConditionQueue(maxsize=1)
+        self._queues['res'] = ConditionQueue(maxsize=1)
+        if work_cb is None:
+            self._queues['out'] = self._queues['in']   # relay without a worker
+        else:
+            self._threads['work'] = TensorWorkThread(self._queues['in'], self._queues['out'], work_cb)
+        if results_cb is not None:
+            queue_res = self._queues['out'] if rank_dst is None else self._queues['res']
+            self._threads['res'] = TensorWorkThread(queue_res, None, results_cb)
+        if rank_dst is not None:
+            self._threads['send'] = TensorSendThread(self._queues['out'], rank_dst)
+        if rank_src is not None:
+            queue_in = self._queues['in'] if results_cb is None else self._queues['res']
+            self._threads['recv'] = TensorRecvThread(queue_in, rank_src)
+
+    def init(self) -> None:
+        """Start the threads."""
+        assert not self._initialized
+        self._initialized = True
+        for thr in self._threads.values():
+            thr.start()
+
+    def shutdown(self) -> None:
+        """Stop and join the threads."""
+        assert self._initialized
+        self._initialized = False
+        for thr in self._threads.values():
+            thr.stop()
+        for thr in self._threads.values():
+            thr.join(timeout=10)
+
+    def register_recv_pre_hook(self, hook: Callable[..., None], args: tuple) -> None:
+        """Register a pre hook for tensor receive with signature: `hook(*args)`."""
+        thr = self._threads.get('recv')
+        if thr is not None:
+            thr.register_pre_hook(hook, args)
+
+    def register_recv_post_hook(self, hook: Callable[..., None], args: tuple) -> None:
+        """Register a post hook for tensor receive with signature: `hook(tensors, *args)`."""
+        thr = self._threads.get('recv')
+        if thr is not None:
+            thr.register_post_hook(hook, args)
+
+    def register_send_pre_hook(self, hook: Callable[..., None], args: tuple) -> None:
+        """Register a pre hook for tensor send with signature: `hook(*args)`."""
+        thr = self._threads.get('send')
+        if thr is not None:
+            thr.register_pre_hook(hook, args)
+
+    def register_send_post_hook(self, hook: Callable[..., None], args: tuple) -> None:
+        """Register a post hook for tensor send with signature: `hook(tensors, *args)`."""
+        thr = self._threads.get('send')
+        if thr is not None:
+            thr.register_post_hook(hook, args)
+
+    def __enter__(self):
+        self.init()
+        return self
+
+    def __exit__(self, *args):
+        self.shutdown()
+
+    def check_workers(self) -> None:
+        """Re-raise an exception that killed a worker thread (the reference would hang instead)."""
+        for thr in self._threads.values():
+            exc = getattr(thr, 'exception', None)
+            if exc is not None:
+                raise RuntimeError("a pipeline worker thread failed") from exc
+
+    def enqueue_tensor(self, tensor: torch.Tensor) -> None:
+        """Insert data into the pipeline; blocks while the inbound queue is full (`p2p/__init__.py:442-450`)."""
+        assert self._initialized
+        queue_in = self._queues['in']
+        with queue_in.condition:
+            while queue_in.full():
+                self.check_workers()
+                queue_in.condition.wait(0.5)
+            queue_in.put(_Payload(tensor))
+            queue_in.condition.notify_all()

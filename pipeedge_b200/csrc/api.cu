@@ -23,6 +23,7 @@ void set_error(const char* fmt, ...) {
 int check_cuda(cudaError_t err, const char* what) {
   if (err == cudaSuccess) return PE_OK;
   set_error("CUDA error %d (%s) in %s", static_cast<int>(err), cudaGetErrorString(err), what);
+  cudaGetLastError();  // consume it: a stale error must not be blamed on the next, unrelated call
   return PE_ERR_CUDA;
 }
 

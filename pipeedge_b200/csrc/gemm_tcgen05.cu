@@ -317,7 +317,8 @@ int choose_block_n(int m, int n) {
 template <int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   static bool configured = false;
-  const int max_smem = 227 * 1024;
+  // the attribute bounds DYNAMIC shared memory; static barriers live outside it (227 KiB total per CTA)
+  const int max_smem = kPipeSmemBudget + 2048;
   if (!configured) {
     PE_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     configured = true;

@@ -46,6 +46,7 @@ struct pe_stage {
   __half* inter16 = nullptr;
   float* t32 = nullptr;
   int kernels_last = 0;
+  cudaStream_t capture_stream = nullptr;  // private stream the kernel sequence is captured on
   typedef std::tuple<int, const void*, const void*, void*, void*> Key;
   struct Cached {
     cudaGraphExec_t exec = nullptr;
@@ -239,6 +240,7 @@ int pe_stage_destroy(pe_stage* st) {
   if (st == nullptr) return PE_OK;
   for (auto& kv : st->graphs)
     if (kv.second.exec != nullptr) cudaGraphExecDestroy(kv.second.exec);
+  if (st->capture_stream != nullptr) cudaStreamDestroy(st->capture_stream);
   cudaFree(st->a16);
   cudaFree(st->qkv16);
   cudaFree(st->ctx16);
@@ -268,12 +270,18 @@ int pe_stage_forward(pe_stage* st, const void* in0, const void* in1, void* out0,
     c.warmed = true;
     return enqueue(st, in0, in1, out0, out1, ubatch, stream, &st->kernels_last);
   }
-  // second use: capture the same sequence, instantiate, launch
+  // second use: capture the same sequence on the stage's private stream (the caller's stream may be the
+  // legacy default stream, which cannot be captured), instantiate, then launch into the caller's stream
+  if (st->graphs.size() > 64) {  // pointers that never repeat would grow the cache without bound
+    for (auto& kv : st->graphs)
+      if (kv.second.exec != nullptr && &kv.second != &c) { cudaGraphExecDestroy(kv.second.exec); kv.second.exec = nullptr; }
+  }
+  if (st->capture_stream == nullptr) PE_CUDA(cudaStreamCreateWithFlags(&st->capture_stream, cudaStreamNonBlocking));
   cudaGraph_t graph = nullptr;
-  PE_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+  PE_CUDA(cudaStreamBeginCapture(st->capture_stream, cudaStreamCaptureModeThreadLocal));
   int n_k = 0;
-  const int rc = enqueue(st, in0, in1, out0, out1, ubatch, stream, &n_k);
-  const cudaError_t end = cudaStreamEndCapture(stream, &graph);
+  const int rc = enqueue(st, in0, in1, out0, out1, ubatch, st->capture_stream, &n_k);
+  const cudaError_t end = cudaStreamEndCapture(st->capture_stream, &graph);
   if (rc != PE_OK) {
     if (graph != nullptr) cudaGraphDestroy(graph);
     return rc;

@@ -39,14 +39,18 @@ def test_gelu_clamp_branch(q, bit):
     threshold is held to 2 ulp and the codes to exact equality only when the threshold matches bit for bit."""
     basic_op, clamp_op = q
     from pipeedge_b200 import ops
+    from oracle import quant as oq
     x = torch.from_numpy(QG['x_g']).cuda()
     _, _, _, alpha = ops.quant_encode(x, bit, True)
-    want_alpha = np.float32(QG[f"alpha_g_{bit}"])
+    want_alpha, kind = oq.clamp_alpha(x.cpu(), bit)
+    assert kind == 'gelu'
     got_alpha = np.float32(alpha.item())
     assert abs(float(got_alpha) - float(want_alpha)) <= 2 * np.spacing(want_alpha)
     enc = basic_op.tensor_encode_outerdim(x, bit, clamp=True)
-    if got_alpha == want_alpha:
+    if got_alpha == want_alpha or float(x.abs().max()) < min(float(got_alpha), float(want_alpha)):
+        # same threshold, or a threshold that clamps nothing: the reference's codes must be reproduced exactly
         np.testing.assert_array_equal(enc[0].cpu().numpy(), QG[f"comm_g_{bit}"])
+        np.testing.assert_array_equal(enc[2].cpu().numpy(), QG[f"scale_g_{bit}"])
     clamped = clamp_op.clamp_banner2019_gelu(x, bit)
     assert float(clamped.max()) <= float(got_alpha)
 
@@ -82,7 +86,8 @@ def test_full_size_against_oracle(q, shape, bit):
     alpha, _ = oq.clamp_alpha(x, bit)
     xc = x.clamp(-float(alpha), float(alpha))
     step = enc[2].cpu().view(-1, *([1] * (x.dim() - 1))) / ((1 << bit) - 1)
-    assert torch.all((dec - xc).abs() <= 0.5 * step * 1.0001 + 1e-6)
+    slack = 8 * float(np.finfo(np.float32).eps) * float(x.abs().max())   # fp32 rounding of scale/shift arithmetic
+    assert torch.all((dec - xc).abs() <= 0.5 * step * 1.0001 + slack)
 
 
 def test_no_clamp_is_bare_tensor_encode_outerdim(q):
