@@ -1,0 +1,511 @@
+#!/usr/bin/env python
+"""Headline benchmark: pipelined ViT / BERT / DeiT inference throughput on N B200s (one stage per GPU).
+
+    python bench.py --gpus 1 --steps 200 --warmup 20                       # N = 1
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W                             # N > 1, one rank per GPU
+    python bench.py --impl reference --gpus N --steps K --warmup W         # the reference's CPU path
+
+A STEP is one micro-batch through the whole pipeline (BASELINE.json: images/s or sequences/s per pipeline).
+Default workload = BASELINE.json configs[1]'s model and micro-batch (google/vit-base-patch16-224, ubatch 8,
+fp16 operands / fp32 accumulate) with the 48 sub-layers split evenly over the N stages ([1,24,25,48] at N=2).
+
+One JSON line is printed by rank 0:
+  value        whole-pipeline throughput with inputs already resident in HBM (CUDA-event timed, max over ranks)
+  e2e          the same through the public API with pinned HOST inputs: H2D of every micro-batch and D2H of
+               every result inside the timed region
+  roofline     the dominant kernel (the FC1 tcgen05 GEMM): algorithmic FLOPs per launch / its CUDA-event
+               duration inside a live forward, against MEASURED_PEAKS.json
+  cpu_baseline the CPU oracle port (oracle/shards.py, torch fp32 on all host cores) on a bounded sample
+`--impl reference` times that CPU port as the reference arm (the reference is Python and cannot travel to
+the GPU box).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from pipeedge_b200.synth import MODEL_SPECS, hf_config, synth_input, synth_weights  # noqa: E402
+
+WORKLOADS = {
+    # name: (model, ubatch, seq_len, quant bits per hop, metric, unit)
+    'vit-base': ('google/vit-base-patch16-224', 8, 0, 0, 'images/sec per pipeline', 'images/s'),
+    'vit-large': ('google/vit-large-patch16-224', 16, 0, 0, 'images/sec per pipeline', 'images/s'),
+    'bert-base': ('textattack/bert-base-uncased-CoLA', 32, 128, 0, 'sequences/sec per pipeline', 'sequences/s'),
+    'deit-base-q8': ('facebook/deit-base-distilled-patch16-224', 32, 0, 8, 'images/sec per pipeline', 'images/s'),
+}
+N_INPUTS = 16   # distinct resident micro-batches the timed loop rotates over
+
+
+def even_partition(layers: int, n: int):
+    """Split `layers` sub-layers into n contiguous 1-based inclusive ranges, as even as possible."""
+    base, rem = divmod(layers, n)
+    out, cur = [], 1
+    for i in range(n):
+        size = base + (1 if i < rem else 0)
+        out.append((cur, cur + size - 1))
+        cur += size
+    return out
+
+
+def flops_per_item(spec, seq: int) -> float:
+    """GEMMs + QK^T/PV only: L * [S*(2*H*3H + 2*H*H + 2*2*H*I) + 4*S^2*H]."""
+    h, i = spec.hidden, spec.inter
+    return spec.blocks * (seq * (2 * h * 3 * h + 2 * h * h + 4 * h * i) + 4 * seq * seq * h)
+
+
+class ClockSampler:
+    """Samples nvidia-smi SM clocks and throttle reasons while the timed region runs."""
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.QUERY}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self) -> dict:
+        sm, mx, reasons = [], 0, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = max(mx, float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': mx or None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def load_peaks() -> dict:
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path, encoding='utf-8') as fh:
+            peaks = json.load(fh)
+        peaks['source'] = 'measured'
+        return peaks
+    # /opt/skills/guides/B200_PROFILING.md fallback
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port, timed (cpu_baseline and --impl reference)
+# ---------------------------------------------------------------------------------------------------
+def cpu_forward_timer(spec, ubatch: int, seq: int):
+    """Returns (callable running one micro-batch through the whole model on the CPU, cores used)."""
+    from oracle import shards as osh   # the one place bench.py may execute oracle/ (as the timed CPU baseline)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    weights = synth_weights(spec, seed=0)
+    model = osh.PreparedShard(spec, weights, 1, spec.layers)
+    x = synth_input(spec, ubatch, seed=1, seq_len=seq or 128)
+    return (lambda: model.forward(x)), cores
+
+
+def cpu_baseline(spec, ubatch: int, seq: int, unit: str, budget_s: float = 15.0) -> dict:
+    fwd, cores = cpu_forward_timer(spec, ubatch, seq)
+    fwd()   # warm-up (thread pool, oneDNN primitive caches)
+    t0 = time.perf_counter()
+    n = 0
+    while n < 2 or (time.perf_counter() - t0 < budget_s and n < 64):
+        fwd()
+        n += 1
+    dt = time.perf_counter() - t0
+    return {'value': n * ubatch / dt, 'unit': unit, 'cores': cores, 'kind': 'port',
+            'sample': f"{n} micro-batches of {ubatch} through all {spec.layers} sub-layers, torch fp32 CPU "
+                      f"({dt:.1f} s), 1 process x {cores} threads"}
+
+
+def run_reference_arm(args, spec, ubatch, seq, metric, unit, workload):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return   # the CPU arm is a single process using every host core; other ranks have no work
+    fwd, cores = cpu_forward_timer(spec, ubatch, seq)
+    steps = max(1, args.steps)
+    for _ in range(max(1, min(args.warmup, 2))):
+        fwd()
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):   # bounded so the whole arm ends within a few minutes
+        fwd()
+        done += 1
+        if time.perf_counter() - t0 > 120:
+            break
+    dt = time.perf_counter() - t0
+    value = done * ubatch / dt
+    sample = f"{done} micro-batches of {ubatch} (of {steps} requested), torch fp32 CPU, {cores} threads"
+    print(json.dumps({
+        'impl': 'reference', 'metric': metric, 'value': value, 'unit': unit, 'n_gpus': args.gpus, 'steps': done,
+        'warmup': args.warmup, 'ms_per_step': dt / done * 1e3, 'higher_is_better': True, 'scaling': 'strong',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': workload, 'model': spec.name, 'ubatch': ubatch, 'seq_len': seq or spec.tokens,
+                   'note': "CPU port of the reference path (oracle/shards.py); the reference package is Python and "
+                           "cannot travel to the GPU box"},
+        'cpu_baseline': {'value': value, 'unit': unit, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def make_shard(spec, weights, layer_start, layer_end):
+    from pipeedge_b200.models import ModuleShardConfig
+    from pipeedge_b200.models.transformers import bert, deit, vit
+    classes = {'vit': vit.ViTShardForImageClassification, 'deit': deit.DeiTShardForImageClassification,
+               'bert': bert.BertShardForSequenceClassification}
+    cfg = ModuleShardConfig(layer_start=layer_start, layer_end=layer_end, is_first=layer_start == 1,
+                            is_last=layer_end == spec.layers)
+    return classes[spec.family](hf_config(spec), cfg, weights)
+
+
+def roofline_from_profile(shard, sample, spec, ubatch, seq, peaks) -> dict:
+    """Per-kernel CUDA-event times of live eager forwards -> roofline of the dominant kernel (FC1 GEMM)."""
+    stage = shard.stage
+    acc = {}
+    for _ in range(3):
+        for kind, ms in stage.profile(sample):
+            acc.setdefault(kind, []).append(ms)
+    m = ubatch * seq
+    h, i = spec.hidden, spec.inter
+    flops = {'gemm_qkv': 2.0 * m * 3 * h * h, 'gemm_out': 2.0 * m * h * h, 'gemm_fc1': 2.0 * m * i * h,
+             'gemm_fc2': 2.0 * m * h * i, 'attention': 4.0 * ubatch * seq * seq * h}
+    breakdown = {}
+    for kind, vals in acc.items():
+        avg_ms = sum(vals) / len(vals)
+        entry = {'launches_per_forward': len(vals) // 3, 'avg_us': avg_ms * 1e3}
+        if kind in flops:
+            entry['tflops'] = flops[kind] / (avg_ms * 1e-3) / 1e12
+        breakdown[kind] = entry
+    total_ms = sum(sum(v) for v in acc.values()) / 3
+    dom = 'gemm_fc1'
+    achieved = breakdown[dom]['tflops']
+    peak = peaks['bf16_tflops_sustained']   # timed inside a long step
+    return {'bound': 'tensor', 'kernel': 'gemm_tcgen05_kernel<PE_EPI_GELU_F16> (FC1)', 'achieved': achieved,
+            'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
+            'peak_source': f"{peaks['source']} bf16_tflops_sustained (MEASURED_PEAKS.json)",
+            'flops_per_launch': flops[dom], 'share_of_step': sum(acc[dom]) / 3 / total_ms,
+            'all_gemm_tflops': sum(flops[k] * breakdown[k]['launches_per_forward'] for k in flops if k in breakdown
+                                   and k.startswith('gemm')) / (sum(sum(acc[k]) for k in acc if k.startswith('gemm'))
+                                                                / 3 * 1e-3) / 1e12,
+            'breakdown': breakdown, 'eager_forward_ms': total_ms}
+
+
+def run_single_gpu(args, spec, ubatch, seq, qbit, metric, unit, workload):
+    from pipeedge_b200 import ops
+    from pipeedge_b200.comm.p2p import DistP2pPipelineStage
+    torch.cuda.set_device(0)
+    dev = torch.device('cuda', 0)
+    weights = synth_weights(spec, seed=0)
+    shard = make_shard(spec, weights, 1, spec.layers)
+    shard.use_cuda_graph = True
+    del weights
+    seq_eff = seq or spec.tokens
+    inputs_host = [synth_input(spec, ubatch, seed=100 + i, seq_len=seq or 128).pin_memory() for i in range(N_INPUTS)]
+    inputs_dev = [x.to(dev) for x in inputs_host]
+    steps, warmup = args.steps, max(3, args.warmup)
+    stream = torch.cuda.Stream(device=dev)
+    results = [None] * 4
+
+    # ---- value: inputs resident in HBM, CUDA-event timed
+    with torch.cuda.stream(stream):
+        for i in range(warmup):
+            results[i % 4] = shard(inputs_dev[i % N_INPUTS])
+        stream.synchronize()
+        launches0 = ops.launch_count()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(0) as clocks:
+            torch.cuda.synchronize()
+            start.record(stream)
+            for i in range(steps):
+                results[i % 4] = shard(inputs_dev[i % N_INPUTS])
+            end.record(stream)
+            torch.cuda.synchronize()
+        ms = start.elapsed_time(end)
+        launches = ops.launch_count() - launches0
+        logits_check = results[(steps - 1) % 4].float().abs().sum().item()
+    value = steps * ubatch / (ms * 1e-3)
+    if args.quick:
+        print(json.dumps({'metric': metric, 'value': value, 'unit': unit, 'n_gpus': 1, 'steps': steps,
+                          'ms_per_step': ms / steps, 'gpu_launches': int(launches), 'quick': True}))
+        return
+
+    # ---- e2e: public API (DistP2pPipelineStage threads), pinned host inputs, D2H of every result
+    done = threading.Event()
+    got = []
+    target = [0]
+
+    def results_cb(t):
+        got.append(t.cpu())        # D2H read of the step's result (logits)
+        if len(got) >= target[0]:
+            done.set()
+
+    shard_e2e = shard
+    with DistP2pPipelineStage(None, None, shard_e2e, results_cb) as stage_ctx:
+        target[0] = warmup
+        for i in range(warmup):
+            stage_ctx.enqueue_tensor(inputs_host[i % N_INPUTS])
+        assert done.wait(300), "e2e warm-up did not finish"
+        stage_ctx.check_workers()
+        got.clear()
+        done.clear()
+        target[0] = steps
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            stage_ctx.enqueue_tensor(inputs_host[i % N_INPUTS])
+        assert done.wait(600), "e2e run did not finish"
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        stage_ctx.check_workers()
+    h2d = inputs_host[0].numel() * inputs_host[0].element_size()
+    d2h = got[0].numel() * got[0].element_size()
+    e2e = {'value': steps * ubatch / e2e_s, 'unit': unit, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+           'ms_per_step': e2e_s / steps * 1e3}
+
+    # ---- roofline of the dominant kernel, from per-kernel events inside live forwards
+    peaks = load_peaks()
+    with torch.cuda.stream(stream):
+        emb = shard.vit._embed(inputs_dev[0]) if spec.family != 'bert' else shard.bert._embed(inputs_dev[0])  # noqa
+        roof = roofline_from_profile(shard, emb, spec, ubatch, seq_eff, peaks)
+    total_flops = flops_per_item(spec, seq_eff)
+
+    out = {
+        'metric': metric, 'value': value, 'unit': unit, 'n_gpus': 1, 'steps': steps, 'warmup': warmup,
+        'ms_per_step': ms / steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'f16', 'data': 'synthetic',
+        'config': {'workload': workload, 'model': spec.name, 'ubatch': ubatch, 'seq_len': seq_eff,
+                   'partition': [1, spec.layers], 'quant': qbit, 'cuda_graph': True,
+                   'l2': f"timed loop rotates over {N_INPUTS} distinct resident micro-batches; fp16 weights of the "
+                         f"stage ({spec.blocks * (4 * spec.hidden ** 2 + 2 * spec.hidden * spec.inter) * 2 / 1e6:.0f} MB) "
+                         "exceed the 126 MB L2 and stream from HBM every step"},
+        'clocks': clocks.summary(), 'e2e': e2e, 'gpu_launches': int(launches),
+        'roofline': roof,
+        'model_tflops': value * total_flops / 1e12,
+        'model_frac_of_sustained_peak': value * total_flops / 1e12 / peaks['bf16_tflops_sustained'],
+        'checksum': logits_check,
+    }
+    if not args.no_cpu_baseline:
+        out['cpu_baseline'] = cpu_baseline(spec, ubatch, seq, unit)
+    print(json.dumps(out))
+
+
+def run_pipeline(args, spec, ubatch, seq, qbit, metric, unit, workload):
+    """N > 1: one stage per rank through DistP2pContext / DistP2pPipelineStage (the runtime.py path)."""
+    import torch.distributed as dist
+    from pipeedge_b200 import ops
+    from pipeedge_b200.comm.p2p import DistP2pContext, DistP2pPipelineStage
+    import runtime as rt
+    rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+    local = int(os.environ.get('LOCAL_RANK', rank))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    parts = even_partition(spec.layers, world)
+    weights = synth_weights(spec, seed=0)
+    shard = make_shard(spec, weights, *parts[rank])
+    shard.use_cuda_graph = True
+    del weights
+    steps, warmup = args.steps, max(3, args.warmup)
+    seq_eff = seq or spec.tokens
+    last = world - 1
+    shard.register_buffer('quant_bit', torch.tensor(qbit if rank != last else 0), persistent=False)
+    if rank != last:
+        shard.register_forward_hook(rt.forward_hook_quant_encode)
+    if rank != 0:
+        shard.register_forward_pre_hook(rt.forward_pre_hook_quant_decode)
+
+    counter = {'n': 0, 'start': None, 'end': None, 'launch0': 0, 'launch1': 0}
+    phase_done = threading.Event()
+    phase = {'target': 0, 'timed': False}
+
+    def work(payload):
+        if phase['timed'] and counter['n'] == 0:
+            counter['start'] = torch.cuda.Event(enable_timing=True)
+            counter['start'].record()
+            counter['launch0'] = ops.launch_count()
+        out = shard(payload)
+        counter['n'] += 1
+        if counter['n'] == phase['target']:
+            if phase['timed']:
+                counter['end'] = torch.cuda.Event(enable_timing=True)
+                counter['end'].record()
+                counter['launch1'] = ops.launch_count()
+            if rank != 0:
+                phase_done.set()
+        return out
+
+    got = []
+    res_done = threading.Event()
+    e2e_mode = {'on': False}
+
+    def results_cb(t):
+        got.append(t.cpu() if e2e_mode['on'] else t)
+        if len(got) >= phase['target']:
+            res_done.set()
+
+    stop = threading.Event()
+    go = threading.Event()
+
+    def handle_cmd(cmd, tensors):
+        if cmd == 0:
+            stop.set()
+        elif cmd == 2:   # next phase: [target, timed]
+            phase['target'], phase['timed'] = int(tensors[0][0]), bool(tensors[0][1])
+            counter['n'] = 0
+            go.set()
+
+    def gather_max(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def gather_sum(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t[0])
+
+    out = None
+    with DistP2pContext(('gloo',), {'world_size': world, 'rank': rank}, handle_cmd) as ctx:
+        src = last if rank == 0 else rank - 1
+        dst = 0 if rank == last else rank + 1
+        with DistP2pPipelineStage(src, dst, work, results_cb if rank == 0 else None) as stage_ctx:
+            inputs_host = inputs_dev = None
+            if rank == 0:
+                inputs_host = [synth_input(spec, ubatch, seed=100 + i, seq_len=seq or 128).pin_memory()
+                               for i in range(N_INPUTS)]
+                inputs_dev = [x.to(dev) for x in inputs_host]
+
+            def run_phase(n, timed, host):
+                """Rank 0 drives: announce the phase, feed n micro-batches, wait for the n results."""
+                dist.barrier()
+                if rank == 0:
+                    phase['target'], phase['timed'] = n, timed
+                    counter['n'] = 0
+                    ctx.cmd_broadcast(2, (torch.tensor([n, int(timed)]),))
+                else:
+                    assert go.wait(600)
+                    go.clear()
+                dist.barrier()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                if rank == 0:
+                    got.clear()
+                    res_done.clear()
+                    e2e_mode['on'] = host
+                    src_list = inputs_host if host else inputs_dev
+                    for i in range(n):
+                        stage_ctx.enqueue_tensor(src_list[i % N_INPUTS])
+                    assert res_done.wait(900), "pipeline results did not arrive"
+                else:
+                    assert phase_done.wait(900), "stage did not finish its micro-batches"
+                    phase_done.clear()
+                torch.cuda.synchronize()
+                wall = time.perf_counter() - t0
+                stage_ctx.check_workers()
+                dist.barrier()
+                return wall
+
+            run_phase(warmup, False, False)
+            with ClockSampler(local) as clocks:
+                run_phase(steps, True, False)
+            dev_ms = counter['start'].elapsed_time(counter['end'])
+            ms = gather_max(dev_ms)
+            launches = gather_sum(counter['launch1'] - counter['launch0'])
+            run_phase(warmup, False, True)
+            e2e_wall = gather_max(run_phase(steps, False, True))
+            if rank == 0:
+                peaks = load_peaks()
+                value = steps * ubatch / (ms * 1e-3)
+                total_flops = flops_per_item(spec, seq_eff)
+                h2d = inputs_host[0].numel() * inputs_host[0].element_size()
+                d2h = got[0].numel() * got[0].element_size()
+                out = {
+                    'metric': metric, 'value': value, 'unit': unit, 'n_gpus': world, 'steps': steps, 'warmup': warmup,
+                    'ms_per_step': ms / steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+                    'dtype': 'f16', 'data': 'synthetic',
+                    'config': {'workload': workload, 'model': spec.name, 'ubatch': ubatch, 'seq_len': seq_eff,
+                               'partition': [list(p) for p in parts], 'quant': qbit, 'cuda_graph': True,
+                               'hop': 'NCCL P2P per-direction communicators, fp32 activations'
+                                      + (f' quantised to {qbit} bits' if qbit else ''),
+                               'l2': f"timed loop rotates over {N_INPUTS} distinct resident micro-batches; per-stage "
+                                     "weights may be L2-resident, as in steady-state serving"},
+                    'clocks': clocks.summary(),
+                    'e2e': {'value': steps * ubatch / e2e_wall, 'unit': unit, 'h2d_bytes_per_step': h2d,
+                            'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_wall / steps * 1e3},
+                    'gpu_launches': int(launches),
+                    'roofline': {'bound': 'tensor', 'kernel': 'stage GEMMs (tcgen05), pipeline aggregate',
+                                 'achieved': value * total_flops / 1e12 / world,
+                                 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
+                                 'frac': value * total_flops / 1e12 / world / peaks['bf16_tflops_sustained'],
+                                 'traffic': None, 'note': 'per-GPU model FLOP rate; per-kernel roofline is in the N=1 line'},
+                }
+            if rank == 0:
+                ctx.cmd_broadcast(0)
+            else:
+                stop.wait(60)
+    if rank == 0 and out is not None:
+        print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=300)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--impl', choices=['ours', 'reference'], default='ours')
+    ap.add_argument('--workload', choices=sorted(WORKLOADS), default='vit-base')
+    ap.add_argument('--ubatch', type=int, default=0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--quick', action='store_true', help='only the resident-input timed loop (for ncu runs)')
+    args = ap.parse_args()
+    model, ubatch, seq, qbit, metric, unit = WORKLOADS[args.workload]
+    ubatch = args.ubatch or ubatch
+    spec = MODEL_SPECS[model]
+    if args.impl == 'reference':
+        if args.steps == 300:
+            args.steps = 24   # a bounded CPU sample by default
+        run_reference_arm(args, spec, ubatch, seq, metric, unit, args.workload)
+        return
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - pipeedge_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    if world > 1:
+        run_pipeline(args, spec, ubatch, seq, qbit, metric, unit, args.workload)
+    else:
+        run_single_gpu(args, spec, ubatch, seq, qbit, metric, unit, args.workload)
+
+
+if __name__ == '__main__':
+    main()

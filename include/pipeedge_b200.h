@@ -157,6 +157,17 @@ int pe_stage_destroy(pe_stage* stage);
  * (ubatch, pointers) tuple is captured into a CUDA graph on first use and replayed afterwards. */
 int pe_stage_forward(pe_stage* stage, const void* in0, const void* in1, void* out0, void* out1, int ubatch,
                      int use_graph, void* stream);
+/* One EAGER forward with a CUDA event after every kernel: ms_out[i] = device time of kernel i,
+ * kinds_out[i] = PE_KERNEL_* (up to `capacity` entries, *n_out = kernels launched). Synchronises `stream`. */
+#define PE_KERNEL_CAST 0
+#define PE_KERNEL_LAYERNORM 1
+#define PE_KERNEL_GEMM_QKV 2
+#define PE_KERNEL_ATTENTION 3
+#define PE_KERNEL_GEMM_OUT 4
+#define PE_KERNEL_GEMM_FC1 5
+#define PE_KERNEL_GEMM_FC2 6
+int pe_stage_profile(pe_stage* stage, const void* in0, const void* in1, void* out0, void* out1, int ubatch,
+                     void* stream, float* ms_out, int* kinds_out, int capacity, int* n_out);
 /* Number of kernels one pe_stage_forward enqueues for `ubatch` items (for bench.py's gpu_launches). */
 int pe_stage_kernel_count(const pe_stage* stage);
 

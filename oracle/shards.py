@@ -133,29 +133,35 @@ def sublayer_ranges(layer_start: int, layer_end: int):
     return out
 
 
-def embeddings(spec, weights: Mapping, data: torch.Tensor) -> torch.Tensor:
-    """Stage-0 embeddings: HF `ViTEmbeddings` / `DeiTEmbeddings` / `BertEmbeddings` (eval mode)."""
+def embedding_params(spec, weights: Mapping) -> dict:
+    """Stage-0 embedding tensors converted once (`_load_weights_first`: `vit.py:120-130`, `deit.py:119-124`,
+    `bert.py:104-111`)."""
     if spec.family == 'vit':
-        conv_w = _t(np.transpose(weights["embedding/kernel"], [3, 2, 0, 1]))
-        x = F.conv2d(data, conv_w, _t(weights["embedding/bias"]), stride=spec.patch)
-        x = x.flatten(2).transpose(1, 2)
-        cls = _t(weights["cls"]).expand(x.shape[0], -1, -1)
-        return torch.cat((cls, x), dim=1) + _t(weights["Transformer/posembed_input/pos_embedding"])
+        return {'conv_w': _t(np.transpose(weights["embedding/kernel"], [3, 2, 0, 1])), 'conv_b': _t(weights["embedding/bias"]),
+                'cls': _t(weights["cls"]), 'pos': _t(weights["Transformer/posembed_input/pos_embedding"])}
     if spec.family == 'deit':
-        x = F.conv2d(data, _t(weights["patch_embed.proj.weight"]), _t(weights["patch_embed.proj.bias"]),
-                     stride=spec.patch)
-        x = x.flatten(2).transpose(1, 2)
-        cls = _t(weights["cls_token"]).expand(x.shape[0], -1, -1)
         # the reference never loads the distillation token: it stays zeros (deit.py:119-124)
-        dist = torch.zeros_like(cls)
-        return torch.cat((cls, dist, x), dim=1) + _t(weights["pos_embed"])
+        return {'conv_w': _t(weights["patch_embed.proj.weight"]), 'conv_b': _t(weights["patch_embed.proj.bias"]),
+                'cls': _t(weights["cls_token"]), 'pos': _t(weights["pos_embed"])}
+    return {'pos_ids': torch.from_numpy(np.asarray(weights["embeddings.position_ids"])),
+            'word': _t(weights["embeddings.word_embeddings.weight"]),
+            'type': _t(weights["embeddings.token_type_embeddings.weight"]),
+            'pos': _t(weights["embeddings.position_embeddings.weight"]),
+            'ln_w': _t(weights["embeddings.LayerNorm.weight"]), 'ln_b': _t(weights["embeddings.LayerNorm.bias"])}
+
+
+def embeddings(spec, e: dict, data: torch.Tensor) -> torch.Tensor:
+    """Stage-0 embeddings: HF `ViTEmbeddings` / `DeiTEmbeddings` / `BertEmbeddings` (eval mode) over the
+    tensors of `embedding_params`."""
+    if spec.family in ('vit', 'deit'):
+        x = F.conv2d(data, e['conv_w'], e['conv_b'], stride=spec.patch).flatten(2).transpose(1, 2)
+        cls = e['cls'].expand(x.shape[0], -1, -1)
+        prefix = (cls,) if spec.family == 'vit' else (cls, torch.zeros_like(cls))
+        return torch.cat(prefix + (x,), dim=1) + e['pos']
     s = data.shape[1]
-    pos_ids = torch.from_numpy(np.asarray(weights["embeddings.position_ids"]))[:, :s]
-    x = F.embedding(data, _t(weights["embeddings.word_embeddings.weight"]))
-    x = x + _t(weights["embeddings.token_type_embeddings.weight"])[0]
-    x = x + F.embedding(pos_ids, _t(weights["embeddings.position_embeddings.weight"]))
-    return F.layer_norm(x, (spec.hidden,), _t(weights["embeddings.LayerNorm.weight"]),
-                        _t(weights["embeddings.LayerNorm.bias"]), spec.eps)
+    x = F.embedding(data, e['word']) + e['type'][0]
+    x = x + F.embedding(e['pos_ids'][:, :s], e['pos'])
+    return F.layer_norm(x, (spec.hidden,), e['ln_w'], e['ln_b'], spec.eps)
 
 
 def _bert_inner(spec, weights: Mapping) -> Mapping:
@@ -164,7 +170,56 @@ def _bert_inner(spec, weights: Mapping) -> Mapping:
     return weights
 
 
-@torch.no_grad()
+class PreparedShard:
+    """A shard with its weights converted once (what the reference's constructors do at load time), so that
+    repeated forwards cost only the arithmetic. Used for the timed CPU baseline in bench.py."""
+
+    def __init__(self, spec, weights: Mapping, layer_start: int, layer_end: int):
+        self.spec = spec
+        self.layer_start, self.layer_end = layer_start, layer_end
+        self.is_first, self.is_last = layer_start == 1, layer_end == spec.layers   # model_cfg.py:87-90
+        inner = _bert_inner(spec, weights)
+        self.ranges = sublayer_ranges(layer_start, layer_end)
+        self.params = {block: block_params(spec.family, inner, block, spec.hidden) for block, _, _ in self.ranges}
+        self.embed_weights = embedding_params(spec, inner) if self.is_first else None
+        self.head = None
+        if self.is_last:
+            if spec.family == 'vit':
+                self.head = (_t(weights["Transformer/encoder_norm/scale"]), _t(weights["Transformer/encoder_norm/bias"]),
+                             _t(np.transpose(weights["head/kernel"])), _t(weights["head/bias"]))
+            elif spec.family == 'deit':
+                self.head = (_t(weights["norm.weight"]), _t(weights["norm.bias"]), _t(weights["head.weight"]),
+                             _t(weights["head.bias"]))
+            else:
+                self.head = (_t(inner["pooler.dense.weight"]), _t(inner["pooler.dense.bias"]),
+                             _t(weights["classifier.weight"]) if spec.classify else None,
+                             _t(weights["classifier.bias"]) if spec.classify else None)
+
+    @torch.no_grad()
+    def forward(self, data: ShardData, boundaries: dict = None) -> ShardData:
+        """Forward of sub-layers `[layer_start, layer_end]`; see `shard_forward`."""
+        spec = self.spec
+        if self.is_first:
+            data = embeddings(spec, self.embed_weights, data)
+        for block, s0, s1 in self.ranges:
+            p = self.params[block]
+            for sub in range(s0, s1 + 1):
+                data = block_sublayers(spec.family, data, p, spec.heads, spec.eps, sub, sub)
+                if boundaries is not None:
+                    boundaries[block * 4 + sub + 1] = data
+        if self.is_last:
+            if spec.family in ('vit', 'deit'):
+                ln_w, ln_b, head_w, head_b = self.head
+                data = F.layer_norm(data, (spec.hidden,), ln_w, ln_b, spec.eps)
+                data = F.linear(data[:, 0, :], head_w, head_b)
+            else:
+                pool_w, pool_b, cls_w, cls_b = self.head
+                data = torch.tanh(F.linear(data[:, 0], pool_w, pool_b))
+                if cls_w is not None:
+                    data = F.linear(data, cls_w, cls_b)
+        return data
+
+
 def shard_forward(spec, weights: Mapping, layer_start: int, layer_end: int, data: ShardData,
                   boundaries: dict = None) -> ShardData:
     """Forward of the shard covering sub-layers `[layer_start, layer_end]` (1-based, inclusive).
@@ -172,27 +227,4 @@ def shard_forward(spec, weights: Mapping, layer_start: int, layer_end: int, data
     `is_first`/`is_last` follow `model_cfg.py:87-90`. If `boundaries` is a dict, the value after
     every sub-layer `l` is recorded under key `l` (tuples kept as tuples).
     """
-    inner = _bert_inner(spec, weights)
-    is_first, is_last = layer_start == 1, layer_end == spec.layers
-    if is_first:
-        data = embeddings(spec, inner, data)
-    for block, s0, s1 in sublayer_ranges(layer_start, layer_end):
-        p = block_params(spec.family, inner, block, spec.hidden)
-        for sub in range(s0, s1 + 1):
-            data = block_sublayers(spec.family, data, p, spec.heads, spec.eps, sub, sub)
-            if boundaries is not None:
-                boundaries[block * 4 + sub + 1] = data
-    if is_last:
-        if spec.family == 'vit':
-            data = F.layer_norm(data, (spec.hidden,), _t(weights["Transformer/encoder_norm/scale"]),
-                                _t(weights["Transformer/encoder_norm/bias"]), spec.eps)
-            data = F.linear(data[:, 0, :], _t(np.transpose(weights["head/kernel"])), _t(weights["head/bias"]))
-        elif spec.family == 'deit':
-            data = F.layer_norm(data, (spec.hidden,), _t(weights["norm.weight"]), _t(weights["norm.bias"]),
-                                spec.eps)
-            data = F.linear(data[:, 0, :], _t(weights["head.weight"]), _t(weights["head.bias"]))
-        else:
-            data = torch.tanh(F.linear(data[:, 0], _t(inner["pooler.dense.weight"]), _t(inner["pooler.dense.bias"])))
-            if spec.classify:
-                data = F.linear(data, _t(weights["classifier.weight"]), _t(weights["classifier.bias"]))
-    return data
+    return PreparedShard(spec, weights, layer_start, layer_end).forward(data, boundaries)

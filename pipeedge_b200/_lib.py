@@ -51,6 +51,8 @@ SYMBOLS = {
     'pe_stage_create': (c_int, [POINTER(StageDesc), POINTER(BlockWeights), c_int, POINTER(c_void_p)]),
     'pe_stage_destroy': (c_int, [c_void_p]),
     'pe_stage_forward': (c_int, [c_void_p] * 5 + [c_int, c_int, c_void_p]),
+    'pe_stage_profile': (c_int, [c_void_p] * 5 + [c_int, c_void_p, POINTER(c_float), POINTER(c_int), c_int,
+                                 POINTER(c_int)]),
     'pe_stage_kernel_count': (c_int, [c_void_p]),
     'pe_patch_embed': (c_int, [c_void_p] * 7 + [c_int] * 6 + [c_void_p]),
     'pe_bert_embed': (c_int, [c_void_p] * 7 + [c_float, c_void_p, c_int, c_int, c_int, c_void_p]),

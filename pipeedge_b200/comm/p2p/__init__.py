@@ -28,7 +28,7 @@ import torch.distributed as dist
 from .. import DistCmdHandler, DistContext
 
 # Gloo message tags
-TAG_CMD = 10          # [cmd, n_tensors]
+TAG_CMD = 10          # [cmd, n_tensors, sender rank]
 TAG_CMD_META = 11     # per command tensor: [n_bytes] then pickled (dtype, shape)
 TAG_CMD_DATA = 12
 TAG_DATA_HDR = 0      # [header_bytes]; 0 = same header as the previous payload on this hop
@@ -108,7 +108,7 @@ class DistP2pContext(DistContext):
         """Broadcast a command with optional (CPU) tensors to every other rank (`p2p/__init__.py:72-85`)."""
         assert self._initialized
         tensors = () if tensors is None else tuple(tensors)
-        head = torch.tensor([cmd, len(tensors)], dtype=torch.int)
+        head = torch.tensor([cmd, len(tensors), self._rank], dtype=torch.int)
         reqs = []
         keep = []
         for dst in range(self._world_size):
@@ -128,13 +128,33 @@ class DistP2pContext(DistContext):
             req.wait()
 
 
+class _RequestWaiter(threading.Thread):
+    """Blocks in `req.wait()` on a daemon thread so that the owner can poll and still stop cleanly:
+    `is_completed()` never turns true for a Gloo irecv and `wait()` cannot be interrupted (the reference works
+    around the same PyTorch behaviour, `p2p/util.py:8-24`)."""
+
+    def __init__(self, req):
+        super().__init__(daemon=True)
+        self._req = req
+        self.done = threading.Event()
+        self.error: Optional[BaseException] = None
+
+    def run(self):
+        try:
+            self._req.wait()
+        except BaseException as exc:   # pylint: disable=broad-except
+            self.error = exc           # e.g. the process group was destroyed under us at shutdown
+        self.done.set()
+
+
 def _poll(req, stop_evt: threading.Event) -> bool:
-    """Wait for a distributed request, giving up (False) when `stop_evt` is set."""
-    while not req.is_completed():
+    """Wait for a distributed request, giving up (False) when `stop_evt` is set or the request failed."""
+    waiter = _RequestWaiter(req)
+    waiter.start()
+    while not waiter.done.wait(_POLL_SEC * 5):
         if stop_evt.is_set():
             return False
-        time.sleep(_POLL_SEC)
-    return True
+    return waiter.error is None
 
 
 class AbstractTensorExchangeThread(threading.Thread):
@@ -411,13 +431,10 @@ class CommandThread(threading.Thread):
     def run(self):
         """Listen for commands."""
         while True:
-            head = torch.zeros(2, dtype=torch.int)
-            req = dist.irecv(head, tag=TAG_CMD)
-            while not req.is_completed():
-                if self._evt_stop_thread.is_set():
-                    return
-                time.sleep(0.01)
-            src = req.source_rank() if hasattr(req, 'source_rank') else None
+            head = torch.zeros(3, dtype=torch.int)
+            if not _poll(dist.irecv(head, tag=TAG_CMD), self._evt_stop_thread):
+                return
+            src = int(head[2])   # the sender names itself: any-source requests do not report their source
             cmd, count = int(head[0]), int(head[1])
             tensors = ()
             for _ in range(count):

@@ -122,4 +122,17 @@ int cast_impl(const void* src, void* dst, size_t n, bool to_half, cudaStream_t s
   return PE_OK;
 }
 
+// Busy-wait kernel: keeps the stream occupied for ~ms so that work enqueued behind it is fully queued
+// before it starts (used by pe_stage_profile to keep host launch latency out of per-kernel timings).
+__global__ void spin_kernel(long long cycles) {
+  const long long t0 = clock64();
+  while (clock64() - t0 < cycles) {}
+}
+
+int spin_impl(float ms, cudaStream_t stream) {
+  spin_kernel<<<1, 1, 0, stream>>>(static_cast<long long>(ms * 1.9e6f));
+  PE_CUDA(cudaGetLastError());
+  return PE_OK;
+}
+
 }  // namespace pe

@@ -28,6 +28,7 @@ int layernorm_impl(const void* x, const void* gamma, const void* beta, float eps
                    int rows, int hidden, cudaStream_t stream);
 int attention_impl(const void* qkv, void* ctx, int batch, int tokens, int heads, int head_dim, cudaStream_t stream);
 int cast_impl(const void* src, void* dst, size_t n, bool to_half, cudaStream_t stream);
+int spin_impl(float ms, cudaStream_t stream);
 
 struct SubRange {
   int block;  // index into stage->blocks
@@ -63,6 +64,29 @@ namespace pe {
     if (_rc != PE_OK) return _rc; \
   } while (0)
 
+// Optional per-kernel timing of one eager forward: an event is recorded after every launch.
+struct Prof {
+  std::vector<cudaEvent_t> events;  // events[0] precedes the first kernel
+  std::vector<int> kinds;           // PE_KERNEL_* of kernel i, timed by events[i] -> events[i+1]
+  cudaStream_t stream;
+};
+static int prof_mark(Prof* prof, int kind) {
+  if (prof == nullptr) return PE_OK;
+  cudaEvent_t e;
+  PE_CUDA(cudaEventCreate(&e));
+  PE_CUDA(cudaEventRecord(e, prof->stream));
+  prof->events.push_back(e);
+  if (kind >= 0) prof->kinds.push_back(kind);
+  return PE_OK;
+}
+// launch + count + (optional) mark
+#define PE_K(kind, call)                 \
+  do {                                   \
+    PE_TRY(call);                        \
+    ++n_k;                               \
+    PE_TRY(prof_mark(prof, kind));       \
+  } while (0)
+
 static int lin(const void* a, const void* w, const void* b, const void* resid, void* out, int m, int n, int k, int epi,
                cudaStream_t s) {
   return linear_impl(a, w, b, resid, out, m, n, k, epi, 0, 0, 0, 0, s);
@@ -70,7 +94,7 @@ static int lin(const void* a, const void* w, const void* b, const void* resid, v
 
 // Enqueue the kernel sequence of one forward on `stream`. Returns the number of kernels in *count.
 static int enqueue(pe_stage* st, const void* in0, const void* in1, void* out0, void* out1, int ubatch,
-                   cudaStream_t stream, int* count) {
+                   cudaStream_t stream, int* count, Prof* prof = nullptr) {
   const pe_stage_desc& d = st->d;
   const int H = d.hidden, I = d.inter, S = d.tokens;
   const int M = ubatch * S;
@@ -92,10 +116,10 @@ static int enqueue(pe_stage* st, const void* in0, const void* in1, void* out0, v
   if (first_sub == 0 || first_sub == 2) {
     x = static_cast<const float*>(in0);
   } else if (first_sub == 1) {
-    PE_TRY(cast_impl(in0, st->ctx16, static_cast<size_t>(M) * H, true, stream)); ++n_k;
+    PE_K(PE_KERNEL_CAST, cast_impl(in0, st->ctx16, static_cast<size_t>(M) * H, true, stream));
     skip = static_cast<const float*>(in1);
   } else {
-    PE_TRY(cast_impl(in0, st->inter16, static_cast<size_t>(M) * I, true, stream)); ++n_k;
+    PE_K(PE_KERNEL_CAST, cast_impl(in0, st->inter16, static_cast<size_t>(M) * I, true, stream));
     skip = static_cast<const float*>(in1);
   }
 
@@ -105,43 +129,43 @@ static int enqueue(pe_stage* st, const void* in0, const void* in1, void* out0, v
       switch (sub) {
         case 0: {
           if (post_ln) {
-            if (!a16_valid) { PE_TRY(cast_impl(x, st->a16, static_cast<size_t>(M) * H, true, stream)); ++n_k; }
+            if (!a16_valid) { PE_K(PE_KERNEL_CAST, cast_impl(x, st->a16, static_cast<size_t>(M) * H, true, stream)); }
           } else {
-            PE_TRY(layernorm_impl(x, w.ln1_w, w.ln1_b, d.eps, nullptr, st->a16, M, H, stream)); ++n_k;
+            PE_K(PE_KERNEL_LAYERNORM, layernorm_impl(x, w.ln1_w, w.ln1_b, d.eps, nullptr, st->a16, M, H, stream));
           }
-          PE_TRY(lin(st->a16, w.w_qkv, w.b_qkv, nullptr, st->qkv16, M, 3 * H, H, PE_EPI_F16, stream)); ++n_k;
-          PE_TRY(attention_impl(st->qkv16, st->ctx16, ubatch, S, d.heads, H / d.heads, stream)); ++n_k;
+          PE_K(PE_KERNEL_GEMM_QKV, lin(st->a16, w.w_qkv, w.b_qkv, nullptr, st->qkv16, M, 3 * H, H, PE_EPI_F16, stream));
+          PE_K(PE_KERNEL_ATTENTION, attention_impl(st->qkv16, st->ctx16, ubatch, S, d.heads, H / d.heads, stream));
           skip = x; x = nullptr; a16_valid = false;
           break;
         }
         case 1: {
           if (post_ln) {
-            PE_TRY(lin(st->ctx16, w.w_o, w.b_o, skip, st->t32, M, H, H, PE_EPI_RESID_F32, stream)); ++n_k;
-            PE_TRY(layernorm_impl(st->t32, w.ln1_w, w.ln1_b, d.eps, resid_dest, st->a16, M, H, stream)); ++n_k;
+            PE_K(PE_KERNEL_GEMM_OUT, lin(st->ctx16, w.w_o, w.b_o, skip, st->t32, M, H, H, PE_EPI_RESID_F32, stream));
+            PE_K(PE_KERNEL_LAYERNORM, layernorm_impl(st->t32, w.ln1_w, w.ln1_b, d.eps, resid_dest, st->a16, M, H, stream));
             a16_valid = true;
           } else {
-            PE_TRY(lin(st->ctx16, w.w_o, w.b_o, skip, resid_dest, M, H, H, PE_EPI_RESID_F32, stream)); ++n_k;
+            PE_K(PE_KERNEL_GEMM_OUT, lin(st->ctx16, w.w_o, w.b_o, skip, resid_dest, M, H, H, PE_EPI_RESID_F32, stream));
           }
           x = resid_dest; skip = nullptr;
           break;
         }
         case 2: {
           if (post_ln) {
-            if (!a16_valid) { PE_TRY(cast_impl(x, st->a16, static_cast<size_t>(M) * H, true, stream)); ++n_k; }
+            if (!a16_valid) { PE_K(PE_KERNEL_CAST, cast_impl(x, st->a16, static_cast<size_t>(M) * H, true, stream)); }
           } else {
-            PE_TRY(layernorm_impl(x, w.ln2_w, w.ln2_b, d.eps, nullptr, st->a16, M, H, stream)); ++n_k;
+            PE_K(PE_KERNEL_LAYERNORM, layernorm_impl(x, w.ln2_w, w.ln2_b, d.eps, nullptr, st->a16, M, H, stream));
           }
-          PE_TRY(lin(st->a16, w.w_fc1, w.b_fc1, nullptr, st->inter16, M, I, H, PE_EPI_GELU_F16, stream)); ++n_k;
+          PE_K(PE_KERNEL_GEMM_FC1, lin(st->a16, w.w_fc1, w.b_fc1, nullptr, st->inter16, M, I, H, PE_EPI_GELU_F16, stream));
           skip = x; x = nullptr; a16_valid = false;
           break;
         }
         default: {
           if (post_ln) {
-            PE_TRY(lin(st->inter16, w.w_fc2, w.b_fc2, skip, st->t32, M, H, I, PE_EPI_RESID_F32, stream)); ++n_k;
-            PE_TRY(layernorm_impl(st->t32, w.ln2_w, w.ln2_b, d.eps, resid_dest, st->a16, M, H, stream)); ++n_k;
+            PE_K(PE_KERNEL_GEMM_FC2, lin(st->inter16, w.w_fc2, w.b_fc2, skip, st->t32, M, H, I, PE_EPI_RESID_F32, stream));
+            PE_K(PE_KERNEL_LAYERNORM, layernorm_impl(st->t32, w.ln2_w, w.ln2_b, d.eps, resid_dest, st->a16, M, H, stream));
             a16_valid = true;
           } else {
-            PE_TRY(lin(st->inter16, w.w_fc2, w.b_fc2, skip, resid_dest, M, H, I, PE_EPI_RESID_F32, stream)); ++n_k;
+            PE_K(PE_KERNEL_GEMM_FC2, lin(st->inter16, w.w_fc2, w.b_fc2, skip, resid_dest, M, H, I, PE_EPI_RESID_F32, stream));
           }
           x = resid_dest; skip = nullptr;
           break;
@@ -152,8 +176,8 @@ static int enqueue(pe_stage* st, const void* in0, const void* in1, void* out0, v
 
   if (out_tuple) {
     // (ctx | inter, skip): the f16 operand is widened for the fp32 wire format of the boundary payload
-    if (last_sub == 0) { PE_TRY(cast_impl(st->ctx16, out0, static_cast<size_t>(M) * H, false, stream)); ++n_k; }
-    else { PE_TRY(cast_impl(st->inter16, out0, static_cast<size_t>(M) * I, false, stream)); ++n_k; }
+    if (last_sub == 0) { PE_K(PE_KERNEL_CAST, cast_impl(st->ctx16, out0, static_cast<size_t>(M) * H, false, stream)); }
+    else { PE_K(PE_KERNEL_CAST, cast_impl(st->inter16, out0, static_cast<size_t>(M) * I, false, stream)); }
     if (skip != static_cast<const float*>(out1)) {
       PE_CUDA(cudaMemcpyAsync(out1, skip, static_cast<size_t>(M) * H * sizeof(float), cudaMemcpyDeviceToDevice, stream));
     }
@@ -293,6 +317,37 @@ int pe_stage_forward(pe_stage* st, const void* in0, const void* in1, void* out0,
   st->kernels_last = n_k;
   PE_CUDA(cudaGraphLaunch(c.exec, stream));
   return PE_OK;  // kernels were already counted by enqueue() during capture
+}
+
+int pe_stage_profile(pe_stage* st, const void* in0, const void* in1, void* out0, void* out1, int ubatch,
+                     void* stream_v, float* ms_out, int* kinds_out, int capacity, int* n_out) {
+  using namespace pe;
+  PE_REQUIRE(st && ms_out && kinds_out && n_out, "pe_stage_profile: null pointer");
+  PE_REQUIRE(ubatch > 0 && ubatch <= st->d.max_ubatch, "pe_stage_profile: bad ubatch %d", ubatch);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  Prof prof;
+  prof.stream = stream;
+  // Back-log the stream first so that every event and kernel below is already queued when the GPU reaches it
+  // (otherwise host launch gaps would be charged to the kernels).
+  int rc = spin_impl(4.0f, stream);
+  if (rc != PE_OK) return rc;
+  rc = prof_mark(&prof, -1);
+  int n_k = 0;
+  if (rc == PE_OK) rc = enqueue(st, in0, in1, out0, out1, ubatch, stream, &n_k, &prof);
+  if (rc == PE_OK) rc = check_cuda(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+  int n = 0;
+  if (rc == PE_OK) {
+    n = static_cast<int>(prof.kinds.size());
+    for (int i = 0; i < n && i < capacity; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, prof.events[i], prof.events[i + 1]);
+      ms_out[i] = ms;
+      kinds_out[i] = prof.kinds[i];
+    }
+  }
+  for (cudaEvent_t e : prof.events) cudaEventDestroy(e);
+  *n_out = n;
+  return rc;
 }
 
 int pe_stage_kernel_count(const pe_stage* st) { return st == nullptr ? 0 : st->kernels_last; }

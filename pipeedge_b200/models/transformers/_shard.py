@@ -32,7 +32,10 @@ class GpuTransformerShard(ModuleShard):
         self.num_slots = 4
         self._slot = 0
         self._rings = {}
-        self._stream_warm = False
+        self._copy_stream = None
+        self._h2d_rings = {}
+        self._h2d_count = {}
+        self._pending_h2d = []
         if isinstance(model_weights, str):
             with np.load(model_weights) as weights:
                 self._build_shard(weights)
@@ -57,10 +60,46 @@ class GpuTransformerShard(ModuleShard):
 
     # ------------------------------------------------------------------ payload staging
     def _to_device(self, data: TransformerShardData, dtype=torch.float32) -> TransformerShardData:
-        dev = self.stage.device
         if isinstance(data, torch.Tensor):
-            return data.to(device=dev, dtype=dtype, non_blocking=True).contiguous()
-        return tuple(t.to(device=dev, dtype=dtype, non_blocking=True).contiguous() for t in data)
+            return self._one_to_device(data, dtype, 0)
+        return tuple(self._one_to_device(t, dtype, i) for i, t in enumerate(data))
+
+    def _one_to_device(self, t: torch.Tensor, dtype, pos: int) -> torch.Tensor:
+        dev = self.stage.device
+        if t.is_cuda:
+            return t.to(device=dev, dtype=dtype).contiguous()
+        # Host input (the data rank's images / token ids): copy on a side stream into a small ring of device
+        # buffers so that the H2D of micro-batch i+1 overlaps the kernels of micro-batch i. Replaces
+        # `devices.forward_pre_hook_to_device` (`devices.py:8-16`); pinned host memory makes it truly async.
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        key = ('h2d', pos, tuple(t.shape), dtype)
+        ring = self._h2d_rings.setdefault(key, [])
+        idx = self._h2d_count.get(key, 0)
+        self._h2d_count[key] = idx + 1
+        if len(ring) < 4:
+            ring.append([torch.empty(t.shape, dtype=dtype, device=dev), None])
+        slot = ring[idx % 4]
+        buf, last_use = slot
+        compute = torch.cuda.current_stream()
+        with torch.cuda.stream(self._copy_stream):
+            if last_use is not None:
+                self._copy_stream.wait_event(last_use)   # kernels that read this buffer 4 forwards ago are done
+            buf.copy_(t if t.dtype == dtype else t.to(dtype), non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self._copy_stream)
+        compute.wait_event(done)
+        self._pending_h2d.append(slot)
+        return buf
+
+    def _mark_inputs_consumed(self) -> None:
+        """Record, on the compute stream, that the kernels reading the current host-staged inputs were enqueued."""
+        if self._pending_h2d:
+            evt = torch.cuda.Event()
+            evt.record(torch.cuda.current_stream())
+            for slot in self._pending_h2d:
+                slot[1] = evt
+            self._pending_h2d.clear()
 
     def _ring(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
         """Persistent buffer `name` of the current slot (allocated on first use per shape)."""
@@ -81,6 +120,7 @@ class GpuTransformerShard(ModuleShard):
         in0 = data[0] if isinstance(data, tuple) else data
         out = self._stage_out(in0.shape[0])
         res = self.stage.forward(data, out=out, use_graph=self.use_cuda_graph)
+        self._mark_inputs_consumed()
         if self.use_cuda_graph:
             self._slot = (self._slot + 1) % max(1, self.num_slots)
         return res

@@ -195,6 +195,24 @@ class EncoderStage:
                                    1 if use_graph else 0, torch.cuda.current_stream().cuda_stream))
         return (out0, out1) if self.out_is_tuple else out0
 
+    KERNEL_KINDS = ('cast', 'layernorm', 'gemm_qkv', 'attention', 'gemm_out', 'gemm_fc1', 'gemm_fc2')
+
+    def profile(self, data: ShardData):
+        """One eager forward with a CUDA event after every kernel: list of (kind, milliseconds)."""
+        in0, in1 = data if self.in_is_tuple else (data, None)
+        ubatch = in0.shape[0]
+        s0, s1 = self.out_shapes(ubatch)
+        out0 = torch.empty(s0, dtype=torch.float32, device=self.device)
+        out1 = None if s1 is None else torch.empty(s1, dtype=torch.float32, device=self.device)
+        cap = 16 * len(self.ranges) + 8
+        ms = (ctypes.c_float * cap)()
+        kinds = (ctypes.c_int * cap)()
+        n = ctypes.c_int(0)
+        check(LIB.pe_stage_profile(self._handle, in0.data_ptr(), None if in1 is None else in1.data_ptr(),
+                                   out0.data_ptr(), None if out1 is None else out1.data_ptr(), ubatch,
+                                   torch.cuda.current_stream().cuda_stream, ms, kinds, cap, ctypes.byref(n)))
+        return [(self.KERNEL_KINDS[kinds[i]], float(ms[i])) for i in range(min(n.value, cap))]
+
     def kernel_count(self) -> int:
         """Kernels enqueued by the last forward."""
         return int(LIB.pe_stage_kernel_count(self._handle))

@@ -1,0 +1,317 @@
+"""Distributed pipeline driver application - drop-in for the reference `runtime.py` p2p path.
+
+Same CLI (`runtime.py:610-687`): `runtime.py RANK WORLDSIZE [-d] [-s] [--addr] [--port] [-c p2p] [-m] [-M] [-b]
+[-u] [-pt] [-q] [-r] [-D]`, same schedule semantics (`-pt` 1-based inclusive sub-layer pairs, `-q` bits per
+stage output, `-r` stage-to-rank order, `-D` data rank), same command protocol (CMD_STOP / CMD_SCHED) and the
+same hook structure around the shard (`run_pipeline_p2p`, `runtime.py:418-511`). One rank per B200:
+activations stay in HBM, the hop is NCCL on a side stream, and the QuantPipe hooks call the fused device
+kernels (bit-identical codes). What is NOT carried over (out of scope): the RPC
+backend (`-c rpc`), `sched-pipeline` automated scheduling (`-H/-sm/-sdt/-sd`), monitoring heartbeats, and the
+dataset loaders that need the network; inputs are the reference's synthetic fallback (`runtime.py:386-400`)
+generated locally, weights come from `-M` (an npz in the reference layout) or are synthesised.
+"""
+import argparse
+import logging
+import os
+import queue
+import sys
+import threading
+import time
+from typing import List, Optional, Tuple, Union
+import numpy as np
+import torch
+from torch.utils.data import DataLoader, Dataset
+from pipeedge_b200 import models
+from pipeedge_b200.comm.p2p import DistP2pContext
+from pipeedge_b200.quantization.basic_op import tensor_decode_outerdim, tensor_encode_outerdim
+from pipeedge_b200.synth import MODEL_SPECS, synth_input, synth_weights
+import devices
+import model_cfg
+
+logger = logging.getLogger(__name__)
+
+CMD_STOP = 0
+CMD_SCHED = 1
+
+ENV_SEND_CONSTRAINT: str = "SEND_CONSTRAINT"
+
+
+def forward_hook_quant_encode(module, _input_arg, output: Union[torch.Tensor, Tuple[torch.Tensor, ...]]):
+    """Encode tensors in the forward hook, after the shard (`runtime.py:73-91`).
+
+    Clamp choice, threshold, per-item quantisation and bit-packing run fused on the device; the 5-tensor-per-
+    payload-tensor wire format is the reference's. `quant_bit` is read per call, so adaptive policies may
+    change it between micro-batches."""
+    if isinstance(output, torch.Tensor):
+        output = (output,)
+    assert isinstance(output, tuple)
+    quant_bit = int(module.quant_bit.item())
+    comm_tuple = []
+    for tensor in output:
+        assert isinstance(tensor, torch.Tensor)
+        comm_tuple += tensor_encode_outerdim(tensor, quant_bit, clamp=quant_bit > 0)
+    return tuple(comm_tuple)
+
+
+def forward_pre_hook_quant_decode(_module, input_arg: Tuple[Tuple[torch.Tensor, ...]]):
+    """Decode tensors in the pre-forward hook, before the shard (`runtime.py:93-119`)."""
+    assert isinstance(input_arg, tuple) and len(input_arg) == 1
+    input_tensors = input_arg[0]
+    assert isinstance(input_tensors, tuple)
+    assert len(input_tensors) % 5 == 0 and len(input_tensors) >= 5
+    forward_tensor = [tensor_decode_outerdim(input_tensors[i * 5:i * 5 + 5]) for i in range(len(input_tensors) // 5)]
+    if len(forward_tensor) == 1:
+        return tuple(forward_tensor)        # a single tensor payload
+    return (tuple(forward_tensor),)         # a (data, skip) tuple payload
+
+
+class ThreadSafeCounter:
+    """Thread-safe counter (reference `utils/threads.py:57-91`)."""
+
+    def __init__(self, value: int = 0):
+        self._value = value
+        self._cond = threading.Condition()
+
+    @property
+    def value(self) -> int:
+        """Current counter value."""
+        with self._cond:
+            return self._value
+
+    def add(self, quantity: int = 1) -> None:
+        """Add to counter atomically."""
+        with self._cond:
+            self._value += quantity
+            self._cond.notify_all()
+
+    def wait_gte(self, threshold: int, timeout: Optional[float] = None) -> bool:
+        """Wait until counter >= threshold."""
+        with self._cond:
+            return self._cond.wait_for(lambda: self._value >= threshold, timeout)
+
+
+class RolloverTensorDataset(Dataset):
+    """Like `TensorDataset`, but rolls over when the requested length exceeds the actual length
+    (reference `utils/data.py:7-21`)."""
+
+    def __init__(self, length: int, *tensors: torch.Tensor):
+        assert all(tensors[0].size(0) == t.size(0) for t in tensors), "Size mismatch between tensors"
+        self.length = length
+        self.tensors = tensors
+
+    def __getitem__(self, index):
+        return tuple(t[index % len(t)] for t in self.tensors)
+
+    def __len__(self):
+        return self.length
+
+
+results_counter = ThreadSafeCounter()
+label_queue = queue.Queue()
+
+
+def handle_results(tensors: torch.Tensor) -> None:
+    """Process result tensors (`runtime.py:236-257`): argmax against the queued labels, count items."""
+    n_items = models.get_microbatch_size(tensors, verify=True)
+    if not label_queue.empty():
+        ubatch_labels = label_queue.get()
+        assert len(tensors) == len(ubatch_labels)
+        pred = tensors.argmax(dim=1).cpu()
+        acc = pred.eq(ubatch_labels).sum().item()
+        logger.debug("micro-batch accuracy: %d/%d", acc, n_items)
+    results_counter.add(n_items)
+
+
+def get_pipeline_sched(world_size: int, partition: Optional[List[Tuple[int, int]]], quant: Optional[List[int]],
+                       rank_order: Optional[List[int]], model_name: str) \
+        -> Tuple[List[Tuple[int, int]], List[int], List[int]]:
+    """Get the pipeline schedule: `stage_layers`, `stage_quant`, `stage_ranks` (`runtime.py:291-355`)."""
+    if partition:
+        stage_layers = partition
+        stage_quant = quant if quant else [0] * len(stage_layers)
+        stage_ranks = rank_order if rank_order else list(range(len(stage_layers)))
+    elif quant:
+        raise RuntimeError("Must specify partition with quantization")
+    elif rank_order:
+        raise RuntimeError("Must specify partition with rank stage ordering")
+    elif world_size <= 1:
+        stage_layers = [(1, model_cfg.get_model_layers(model_name))]
+        stage_quant = [0]
+        stage_ranks = [0]
+    else:
+        raise RuntimeError("Automated scheduling (sched-pipeline) is outside this build's scope: pass -pt")
+    logger.info("Scheduling: stage-to-layer mapping: %s", stage_layers)
+    logger.info("Scheduling: stage output quantization: %s", stage_quant)
+    logger.info("Scheduling: stage-to-rank mapping: %s", stage_ranks)
+    return stage_layers, stage_quant, stage_ranks
+
+
+def load_dataset(model_name: str, batch_size: int, ubatch_size: int) -> Dataset:
+    """Synthetic inputs in place of the reference's downloaded image / `bert_input.npz` (`runtime.py:386-400`)."""
+    spec = MODEL_SPECS[model_name]
+    inputs = synth_input(spec, ubatch_size, seed=1)
+    labels = torch.zeros(ubatch_size, dtype=torch.int64)
+    return RolloverTensorDataset(batch_size, inputs, labels)
+
+
+def resolve_weights(model_name: str, model_file: Optional[str]):
+    """`-M` npz path if it exists, else seeded synthetic weights in the same layout (no network here)."""
+    path = model_file or model_cfg.get_model_default_weights_file(model_name)
+    if os.path.exists(path):
+        return path
+    logger.warning("weights file %s not found: using seeded synthetic weights", path)
+    return synth_weights(MODEL_SPECS[model_name], seed=0)
+
+
+sched_q = queue.Queue()
+stop_event = threading.Event()
+
+
+def handle_cmd(cmd: int, tensors: Tuple[torch.Tensor, ...]) -> None:
+    """Process received commands (`runtime.py:406-415`)."""
+    if cmd == CMD_STOP:
+        logger.info("handle_cmd: stop")
+        stop_event.set()
+    elif cmd == CMD_SCHED:
+        logger.info("handle_cmd: sched")
+        sched_q.put(tuple(t.tolist() for t in tensors))
+    else:
+        logger.warning("handle_cmd: Unknown command: %s", cmd)
+
+
+def run_pipeline_p2p(world_size: int, rank: int, model_name: str, model_file: Optional[str], batch_size: int,
+                     ubatch_size: int, partition: Optional[List[Tuple[int, int]]], quant: Optional[List[int]],
+                     rank_order: Optional[List[int]], data_rank: int) -> float:
+    """Run the pipeline using P2P communication (`runtime.py:418-511`); returns throughput on the data rank."""
+    throughput = 0.0
+    with DistP2pContext(('gloo',), {'world_size': world_size, 'rank': rank}, handle_cmd) as dist_ctx:
+        if rank == 0:
+            stage_layers, stage_quant, stage_ranks = get_pipeline_sched(world_size, partition, quant, rank_order,
+                                                                        model_name)
+            dist_ctx.cmd_broadcast(CMD_SCHED, (torch.tensor(stage_layers), torch.tensor(stage_quant),
+                                               torch.tensor(stage_ranks), torch.tensor(data_rank)))
+        else:
+            stage_layers, stage_quant, stage_ranks, data_rank = sched_q.get()
+        try:
+            stage = stage_ranks.index(rank)
+        except ValueError:
+            stage = None
+        if stage is None:
+            model = None
+        else:
+            weights = resolve_weights(model_name, model_file)
+            shard_cls = model_cfg.get_model_dict(model_name)['shard_module']
+            if isinstance(weights, str):
+                model = model_cfg.module_shard_factory(model_name, weights, stage_layers[stage][0],
+                                                       stage_layers[stage][1], stage)
+            else:
+                cfg = models.ModuleShardConfig(layer_start=stage_layers[stage][0], layer_end=stage_layers[stage][1],
+                                               is_first=stage_layers[stage][0] == 1,
+                                               is_last=stage_layers[stage][1] == model_cfg.get_model_layers(model_name))
+                model = shard_cls(model_cfg.get_model_config(model_name), cfg, weights)
+            model.use_cuda_graph = True
+            model.register_buffer('quant_bit', torch.tensor(stage_quant[stage]), persistent=False)
+            send_constraint = float(os.getenv(ENV_SEND_CONSTRAINT, str(0)))
+            model.register_buffer('rate_constraint', torch.tensor(send_constraint), persistent=False)
+            model.register_forward_hook(devices.forward_hook_to_cpu)
+            if stage != len(stage_ranks) - 1:
+                model.register_forward_hook(forward_hook_quant_encode)
+            if stage != 0:
+                model.register_forward_pre_hook(forward_pre_hook_quant_decode)
+            model.register_forward_pre_hook(devices.forward_pre_hook_to_device)
+        with model_cfg.dist_p2p_pipeline_stage_factory(stage_ranks, data_rank, rank, stage, model,
+                                                       handle_results) as stage_ctx:
+            if rank == data_rank:
+                dataset = load_dataset(model_name, batch_size, ubatch_size)
+                data_loader = DataLoader(dataset, batch_size=ubatch_size)
+                tik_data = time.time()
+                start_count = results_counter.value
+                for ubatch, ubatch_labels in data_loader:
+                    label_queue.put(ubatch_labels)
+                    stage_ctx.enqueue_tensor(ubatch)
+                while not results_counter.wait_gte(start_count + len(dataset), timeout=1.0):
+                    stage_ctx.check_workers()
+                latency = time.time() - tik_data
+                throughput = batch_size / latency
+                logger.info("Latency is %f, throughput is %f", latency, throughput)
+                dist_ctx.cmd_broadcast(CMD_STOP)
+                stop_event.set()
+            else:
+                stop_event.wait()
+    return throughput
+
+
+def init_env(device: Optional[str], net_addr: str, net_port: int, net_ifname: str) -> None:
+    """Initialize the PyTorch environment (`runtime.py:581-602`). The compute device is always CUDA here."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("runtime.py: no CUDA device - this build has no CPU fallback")
+    if device is None or device == 'cuda':
+        device = f"cuda:{int(os.environ.get('LOCAL_RANK', '0')) % torch.cuda.device_count()}"
+    devices.DEVICE = torch.device(device)
+    if devices.DEVICE.type != 'cuda':
+        raise RuntimeError(f"runtime.py: device {device} is not a CUDA device")
+    torch.cuda.set_device(devices.DEVICE)
+    os.environ['MASTER_ADDR'] = net_addr
+    os.environ['MASTER_PORT'] = str(net_port)
+    if net_ifname:
+        os.environ["GLOO_SOCKET_IFNAME"] = net_ifname
+
+
+def main() -> None:
+    """Main function (`runtime.py:605-730`)."""
+    parser = argparse.ArgumentParser(description="Pipeline Parallelism Runtime",
+                                     formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    parser.add_argument("rank", type=int, help="the rank for the current node")
+    parser.add_argument("worldsize", type=int, help="the world size (the number of nodes)")
+    parser.add_argument("-d", "--device", type=str, default=None,
+                        help="compute device, e.g.: 'cuda', 'cuda:1' (default: cuda:LOCAL_RANK or cuda:rank)")
+    parser.add_argument("-s", "--socket-ifname", type=str, default="lo", help="socket interface name")
+    parser.add_argument("--addr", type=str, default="127.0.0.1", help="ip address for the master node")
+    parser.add_argument("--port", type=int, default=29500, help="communication port for the master node")
+    parser.add_argument("-c", "--comm", type=str, default="p2p", choices=["p2p"],
+                        help="the communication implementation (rpc is outside this build's scope)")
+    parser.add_argument("-m", "--model-name", type=str, default="google/vit-base-patch16-224",
+                        choices=model_cfg.get_model_names(), help="the neural network model for loading")
+    parser.add_argument("-M", "--model-file", type=str, help="the model file, if not in working directory")
+    parser.add_argument("-b", "--batch-size", default=64, type=int, help="batch size")
+    parser.add_argument("-u", "--ubatch-size", default=8, type=int, help="microbatch size")
+    usched = parser.add_argument_group('User-defined scheduling')
+    usched.add_argument("-pt", "--partition", type=str,
+                        help="comma-delimited list of start/end layer pairs, e.g.: '1,24,25,48'; "
+                             "single-node default: all layers in the model")
+    usched.add_argument("-q", "--quant", type=str,
+                        help="comma-delimited list of quantization bits to use after each stage")
+    usched.add_argument("-r", "--rank-order", type=str, default=None,
+                        help="comma-delimited list of ranks in desired stage order; default: natural rank order")
+    usched.add_argument("-D", "--data-rank", type=int, default=0,
+                        help="rank where inputs are loaded and outputs are processed - must be "
+                             "the same as stage=0 or not in the stage pipeline")
+    args = parser.parse_args()
+
+    if args.partition is None:
+        partition = None
+    else:
+        parts = [int(i) for i in args.partition.split(',')]
+        assert len(parts) % 2 == 0
+        partition = [(parts[i], parts[i + 1]) for i in range(0, len(parts), 2)]
+    quant = None if args.quant is None else [int(i) for i in args.quant.split(',')]
+    rank_order = None if args.rank_order is None else [int(i) for i in args.rank_order.split(',')]
+
+    tik = time.time()
+    device = args.device
+    if device is None and 'LOCAL_RANK' not in os.environ:
+        device = f"cuda:{args.rank % max(1, torch.cuda.device_count())}"
+    init_env(device, args.addr, args.port, args.socket_ifname if args.socket_ifname != 'lo0' else '')
+    logger.info("Device: %s", devices.DEVICE)
+    run_pipeline_p2p(args.worldsize, args.rank, args.model_name, args.model_file, args.batch_size,
+                     args.ubatch_size, partition, quant, rank_order, args.data_rank)
+    logger.info("Total program execution time = %f", time.time() - tik)
+
+
+if __name__ == "__main__":
+    logging.basicConfig(filename='runtime.log', level=logging.DEBUG)
+    console_hndlr = logging.StreamHandler(sys.stdout)
+    console_hndlr.setFormatter(logging.Formatter(fmt='%(message)s'))
+    console_hndlr.setLevel(logging.INFO)
+    logging.getLogger().addHandler(console_hndlr)
+    main()
