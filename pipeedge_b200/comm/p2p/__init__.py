@@ -29,9 +29,10 @@ from .. import DistCmdHandler, DistContext
 
 # Gloo message tags
 TAG_CMD = 10          # [cmd, n_tensors, sender rank]
+_CMD_EXIT = -1        # internal: unblocks the receiver's CommandThread at shutdown
 TAG_CMD_META = 11     # per command tensor: [n_bytes] then pickled (dtype, shape)
 TAG_CMD_DATA = 12
-TAG_DATA_HDR = 0      # [header_bytes]; 0 = same header as the previous payload on this hop
+TAG_DATA_HDR = 0      # [header_bytes]; 0 = same header as the previous payload on this hop; -1 = hop closing
 TAG_DATA_META = 1     # pickled payload description
 TAG_DATA_CPU = 2      # CPU tensors of the payload, in order
 
@@ -88,13 +89,19 @@ class DistP2pContext(DistContext):
                     if src != dst:
                         self._hop_groups[(src, dst)] = dist.new_group(ranks=[src, dst], backend='nccl')
         DistP2pContext._instance = self
-        self._thread_cmd.start()
+        if self._world_size > 1:   # nobody can send a command to a world of one
+            self._thread_cmd.start()
 
     def shutdown(self) -> None:
         """Shutdown threads and the distributed context."""
         super().shutdown()
-        self._thread_cmd.stop()
-        self._thread_cmd.join()
+        if self._world_size > 1:
+            # each rank releases its successor's any-source receive, so no request is left pending
+            self._thread_cmd.stop()
+            dist.send(torch.tensor([_CMD_EXIT, 0, self._rank], dtype=torch.int), dst=(self._rank + 1) % self._world_size,
+                      tag=TAG_CMD)
+            self._thread_cmd.join(timeout=_STOP_GRACE_SEC + 5)
+            dist.barrier()
         DistP2pContext._instance = None
         dist.destroy_process_group()
 
@@ -147,13 +154,23 @@ class _RequestWaiter(threading.Thread):
         self.done.set()
 
 
+_STOP_GRACE_SEC = 10.0
+
+
 def _poll(req, stop_evt: threading.Event) -> bool:
-    """Wait for a distributed request, giving up (False) when `stop_evt` is set or the request failed."""
+    """Wait for a distributed request. Once `stop_evt` is set the peer is expected to unblock us with its
+    closing message; only after a grace period is the request abandoned (False). Abandoning leaves a daemon
+    thread inside `wait()`, which PyTorch turns into an abort at process exit - the reference's teardown race
+     - hence the explicit closing handshake instead."""
     waiter = _RequestWaiter(req)
     waiter.start()
+    deadline = None
     while not waiter.done.wait(_POLL_SEC * 5):
         if stop_evt.is_set():
-            return False
+            if deadline is None:
+                deadline = time.monotonic() + _STOP_GRACE_SEC
+            elif time.monotonic() > deadline:
+                return False
     return waiter.error is None
 
 
@@ -223,6 +240,15 @@ class TensorSendThread(AbstractTensorExchangeThread):
         """Dequeue payloads and send them."""
         self._enter_device()
         group = DistP2pContext.hop_group(dist.get_rank(), self._dst_rank)
+        try:
+            self._run(group)
+        finally:
+            try:   # tell the receiver this hop is closing, so that its pending header receive completes
+                dist.send(torch.tensor([-1], dtype=torch.int64), dst=self._dst_rank, tag=TAG_DATA_HDR)
+            except Exception:   # pylint: disable=broad-except
+                pass
+
+    def _run(self, group):
         while not self._evt_stop_thread.is_set():
             with self._queue_out.condition:
                 while self._queue_out.empty():
@@ -306,6 +332,8 @@ class TensorRecvThread(AbstractTensorExchangeThread):
             hdr = torch.zeros(1, dtype=torch.int64)
             if not _poll(dist.irecv(hdr, src=self._src_rank, tag=TAG_DATA_HDR), self._evt_stop_thread):
                 return
+            if int(hdr[0]) < 0:
+                return   # the sender closed the hop
             if int(hdr[0]) > 0:
                 buf = torch.empty(int(hdr[0]), dtype=torch.uint8)
                 dist.recv(buf, src=self._src_rank, tag=TAG_DATA_META)
@@ -436,6 +464,8 @@ class CommandThread(threading.Thread):
                 return
             src = int(head[2])   # the sender names itself: any-source requests do not report their source
             cmd, count = int(head[0]), int(head[1])
+            if cmd == _CMD_EXIT:
+                return
             tensors = ()
             for _ in range(count):
                 size = torch.zeros(1, dtype=torch.int64)
@@ -493,10 +523,13 @@ class DistP2pPipelineStage:
         """Stop and join the threads."""
         assert self._initialized
         self._initialized = False
-        for thr in self._threads.values():
-            thr.stop()
-        for thr in self._threads.values():
-            thr.join(timeout=10)
+        # workers drain first, then the sender closes its hop (which lets the peer's receiver finish), then our
+        # receiver waits for the upstream sender's closing message
+        for name in ('work', 'res', 'send', 'recv'):
+            thr = self._threads.get(name)
+            if thr is not None:
+                thr.stop()
+                thr.join(timeout=_STOP_GRACE_SEC + 5)
 
     def register_recv_pre_hook(self, hook: Callable[..., None], args: tuple) -> None:
         """Register a pre hook for tensor receive with signature: `hook(*args)`."""

@@ -10,12 +10,20 @@
 //               32-lane quarter and half of the columns), apply bias / GELU / residual, store to HBM,
 //               then hand the accumulator back (`tmem_empty`)
 // Two accumulator stages (2 x 256 TMEM columns) let the epilogue of tile i overlap the MMAs of tile i+1.
-// BN is a RUNTIME multiple of 16 in [16, 256] chosen per problem so the tile count fills 148 SMs in as
-// few waves as possible (these GEMMs are a few microseconds long; wave quantisation dominates).
+//
+// These GEMMs (M = 1.5k..6k tokens, N, K <= 4k) are L2-bandwidth bound with one 128 x BN tile per CTA: every
+// SM re-reads A and W slices out of L2 (r01a ncu: tensor pipe 9-27 % active, ~5 TB/s of L2->SM traffic). So
+// CTAs are launched as thread-block CLUSTERS of CM x CN: the CM CTAs that share a W tile each load 1/CM of
+// it and TMA-MULTICAST it to the others, likewise the CN CTAs sharing an A tile, cutting L2 reads by up to
+// CM (W) and CN (A). Every CTA's `full` barrier sees the bytes of its whole stage whoever issued them; a
+// stage is released to all of its writers at once (tcgen05.commit multicast onto their `empty` barriers).
+// CM, CN and BN (a runtime multiple of 16 in [16, 256]) are chosen per problem by a small cost model:
+// waves x max(tensor time, L2 time).
 //
 // Replaces every nn.Linear on the reference path (see include/pipeedge_b200.h: pe_linear).
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/pipeedge_b200.h"
 #include "common.cuh"
@@ -44,6 +52,8 @@ struct GemmParams {
   int block_n;
   int stages;
   int num_m_blocks, num_n_blocks, num_k_blocks;
+  int cm, cn;                      // cluster shape: CM CTAs along M share a W tile, CN along N share an A tile
+  int num_super_m, num_super_n;    // cluster-level tiles (CM*128 x CN*BN)
   // Optional output-row remap (patch embedding writes token rows 1.. of each item and adds a
   // position table that repeats per item). rows_per_item == 0 disables it.
   int rows_per_item;   // GEMM rows per item
@@ -142,12 +152,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t stage_bytes = kABytes + static_cast<uint32_t>(p.block_n) * (kBlockK * 2);
 
+  // position inside the cluster: rank = m_rank + CM * n_rank
+  const int csize = p.cm * p.cn;
+  const uint32_t crank = csize > 1 ? cluster_ctarank() : 0u;
+  const int m_rank = static_cast<int>(crank) % p.cm;
+  const int n_rank = static_cast<int>(crank) / p.cm;
+  uint16_t row_mask = 0, col_mask = 0;   // CTAs sharing my A tile (same m_rank) / my W tile (same n_rank)
+  for (int c = 0; c < p.cn; ++c) row_mask |= static_cast<uint16_t>(1u << (m_rank + p.cm * c));
+  for (int m = 0; m < p.cm; ++m) col_mask |= static_cast<uint16_t>(1u << (m + p.cm * n_rank));
+  const uint16_t peers_mask = row_mask | col_mask;   // everyone who writes into my stages == everyone I write into
+
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], static_cast<uint32_t>(p.cm + p.cn - 1));
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
@@ -161,24 +181,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();   // peers must not multicast into barriers that are not initialised yet
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int num_supers = p.num_super_m * p.num_super_n;
+  const int cluster_id = static_cast<int>(blockIdx.x) / csize;
+  const int num_clusters = static_cast<int>(gridDim.x) / csize;
+  const int a_slice_rows = kBlockM / p.cn;       // my share of the A tile
+  const int b_slice_rows = p.block_n / p.cm;     // my share of the W tile
 
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------------------ TMA producer
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % p.num_m_blocks;
-        const int n_blk = tile / p.num_m_blocks;
+      for (int sup = cluster_id; sup < num_supers; sup += num_clusters) {
+        const int m_blk = (sup % p.num_super_m) * p.cm + m_rank;
+        const int n_blk = (sup / p.num_super_m) * p.cn + n_rank;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_wait(&empty_bar[stage], phase ^ 1u);   // every CTA I multicast into has drained this stage
           uint8_t* sa = smem_gen + static_cast<size_t>(stage) * stage_bytes;
           mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-          tma_load_2d(sa, &tm_a, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
-          tma_load_2d(sa + kABytes, &tm_b, &full_bar[stage], kb * kBlockK, n_blk * p.block_n);
+          uint8_t* a_dst = sa + static_cast<size_t>(n_rank) * a_slice_rows * (kBlockK * 2);
+          uint8_t* b_dst = sa + kABytes + static_cast<size_t>(m_rank) * b_slice_rows * (kBlockK * 2);
+          const int a_row = m_blk * kBlockM + n_rank * a_slice_rows;
+          const int b_row = n_blk * p.block_n + m_rank * b_slice_rows;
+          if (p.cn > 1) tma_load_2d_multicast(a_dst, &tm_a, &full_bar[stage], kb * kBlockK, a_row, row_mask);
+          else tma_load_2d(a_dst, &tm_a, &full_bar[stage], kb * kBlockK, a_row);
+          if (p.cm > 1) tma_load_2d_multicast(b_dst, &tm_b, &full_bar[stage], kb * kBlockK, b_row, col_mask);
+          else tma_load_2d(b_dst, &tm_b, &full_bar[stage], kb * kBlockK, b_row);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -191,7 +222,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int sup = cluster_id; sup < num_supers; sup += num_clusters) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccStride);
@@ -207,7 +238,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             umma_f16_ss(d_tmem, desc_a + static_cast<uint64_t>(k * 2), desc_b + static_cast<uint64_t>(k * 2), idesc,
                         (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          // release the stage to every CTA that wrote part of it (incl. this one)
+          if (csize > 1) umma_commit_multicast(&empty_bar[stage], peers_mask);
+          else umma_commit(&empty_bar[stage]);
           if (kb == p.num_k_blocks - 1) umma_commit(&tmem_full_bar[acc]);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
@@ -225,9 +258,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     const int c_end = half == 0 ? c_mid : chunks;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile % p.num_m_blocks;
-      const int n_blk = tile / p.num_m_blocks;
+    for (int sup = cluster_id; sup < num_supers; sup += num_clusters) {
+      const int m_blk = (sup % p.num_super_m) * p.cm + m_rank;
+      const int n_blk = (sup / p.num_super_m) * p.cn + n_rank;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
       const int row = m_blk * kBlockM + quarter * 32 + lane;
@@ -250,6 +283,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 
   tcgen05_fence_before();
   __syncthreads();
+  // no CTA may leave while a peer can still multicast into its shared memory or arrive on its barriers
+  if (csize > 1) cluster_sync_all();
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -295,23 +330,46 @@ static int encode_f16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint6
   return PE_OK;
 }
 
-// Pick BN (multiple of 16) minimising waves * per-tile cost; per-tile cost ~ BN MMA columns plus a fixed
-// pipeline-fill/epilogue-drain term. Ties go to the larger tile (fewer A re-reads).
-int choose_block_n(int m, int n) {
-  const int mt = (m + kBlockM - 1) / kBlockM;
-  int best_bn = 16;
+struct GemmPlan {
+  int cm, cn, bn;
+};
+
+static int max_clusters(int csize) {
+  // co-scheduled clusters of 1 CTA/SM kernels: 148 SMs in GPCs of 16-20 (clusters never straddle a GPC)
+  return csize == 1 ? kNumSMs : (csize == 2 ? kNumSMs / 2 : 132 / csize);
+}
+
+// Cost model (SM cycles): waves x max(tensor time of one tile, L2->SM time of one wave's operand reads) + launch.
+// Tensor: 128 x BN x 16 MMA = BN/2 cycles. L2: ~3300 bytes per SM-cycle chip-wide (~6.4 TB/s), the rate the
+// r01a kernels saturated at. A cluster reads (CM*128 + CN*BN) * K * 2 bytes per cluster tile.
+GemmPlan plan_gemm(int m, int n, int k) {
+  int forced[3] = {0, 0, 0};
+  const char* env = getenv("PE_GEMM_FORCE");   // "CM,CN,BN": tuning / debugging only
+  if (env != nullptr && sscanf(env, "%d,%d,%d", &forced[0], &forced[1], &forced[2]) == 3 && forced[0] > 0)
+    return {forced[0], forced[1], forced[2]};
+  GemmPlan best = {1, 1, 16};
   double best_cost = 1e30;
-  for (int bn = 256; bn >= 16; bn -= 16) {
-    const int nt = (n + bn - 1) / bn;
-    const long tiles = static_cast<long>(mt) * nt;
-    const long waves = (tiles + kNumSMs - 1) / kNumSMs;
-    const double cost = static_cast<double>(waves) * (bn + 24.0);
-    if (cost < best_cost - 1e-9) {
-      best_cost = cost;
-      best_bn = bn;
+  const int shapes[5][2] = {{1, 1}, {2, 1}, {1, 2}, {2, 2}, {4, 1}};
+  for (const auto& sh : shapes) {
+    const int cm = sh[0], cn = sh[1], csize = cm * cn;
+    for (int bn = 256; bn >= 16; bn -= 16) {
+      if ((bn / cm) % 8 != 0 || (bn % cm) != 0) continue;   // W slices must keep whole 8-row swizzle atoms
+      const long sm_ = (m + kBlockM * cm - 1) / (kBlockM * cm);
+      const long sn_ = (n + bn * cn - 1) / (bn * cn);
+      const long supers = sm_ * sn_;
+      const long avail = max_clusters(csize);
+      const long waves = (supers + avail - 1) / avail;
+      const long active = supers < avail ? supers : avail;
+      const double tile_cycles = static_cast<double>(k) * bn / 32.0;
+      const double l2_cycles = static_cast<double>(cm * kBlockM + cn * bn) * k * 2.0 * active / 3300.0;
+      const double cost = waves * (tile_cycles > l2_cycles ? tile_cycles : l2_cycles) + 2500.0 + 150.0 * csize;
+      if (cost < best_cost - 1e-9) {
+        best_cost = cost;
+        best = {cm, cn, bn};
+      }
     }
   }
-  return best_bn;
+  return best;
 }
 
 template <int EPI>
@@ -325,10 +383,23 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   }
   const uint32_t stage_bytes = kABytes + static_cast<uint32_t>(p.block_n) * (kBlockK * 2);
   const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + 1024;
-  const int tiles = p.num_m_blocks * p.num_n_blocks;
-  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  gemm_tcgen05_kernel<EPI><<<grid, kGemmThreads, smem, stream>>>(ta, tb, p);
-  PE_CUDA(cudaGetLastError());
+  const int csize = p.cm * p.cn;
+  const int supers = p.num_super_m * p.num_super_n;
+  const int avail = max_clusters(csize);
+  const int clusters = supers < avail ? supers : avail;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(clusters * csize));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(csize);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PE_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<EPI>, ta, tb, p));
   count_launches(1);
   return PE_OK;
 }
@@ -345,27 +416,35 @@ int linear_impl(const void* a, const void* w, const void* bias, const void* resi
   int rc = require_sm100();
   if (rc != PE_OK) return rc;
 
+  const GemmPlan plan = plan_gemm(m, n, k);
+  PE_REQUIRE(plan.bn >= 16 && plan.bn <= 256 && plan.bn % 16 == 0 && plan.cm >= 1 && plan.cn >= 1 &&
+                 plan.cm * plan.cn <= 8 && kBlockM % plan.cn == 0 && (plan.bn / plan.cm) % 8 == 0,
+             "pe_linear: bad tile plan cm=%d cn=%d bn=%d", plan.cm, plan.cn, plan.bn);
   GemmParams p;
   p.bias = static_cast<const float*>(bias);
   p.resid = static_cast<const float*>(resid);
   p.out = out;
   p.m = m; p.n = n; p.k = k;
-  p.block_n = choose_block_n(m, n);
+  p.block_n = plan.bn;
+  p.cm = plan.cm;
+  p.cn = plan.cn;
   const uint32_t stage_bytes = kABytes + static_cast<uint32_t>(p.block_n) * (kBlockK * 2);
   int stages = kPipeSmemBudget / static_cast<int>(stage_bytes);
   p.stages = stages > kMaxStages ? kMaxStages : (stages < 2 ? 2 : stages);
   p.num_m_blocks = (m + kBlockM - 1) / kBlockM;
   p.num_n_blocks = (n + p.block_n - 1) / p.block_n;
   p.num_k_blocks = (k + kBlockK - 1) / kBlockK;
+  p.num_super_m = (p.num_m_blocks + p.cm - 1) / p.cm;
+  p.num_super_n = (p.num_n_blocks + p.cn - 1) / p.cn;
   p.rows_per_item = rows_per_item;
   p.out_item_rows = out_item_rows;
   p.out_row_offset = out_row_offset;
   p.resid_per_item = resid_per_item;
 
-  CUtensorMap ta, tb;
-  rc = encode_f16_2d(&ta, a, static_cast<uint64_t>(m), static_cast<uint64_t>(k), kBlockM);
+  CUtensorMap ta, tb;   // each CTA loads its SLICE of a tile: 128/CN rows of A, BN/CM rows of W
+  rc = encode_f16_2d(&ta, a, static_cast<uint64_t>(m), static_cast<uint64_t>(k), static_cast<uint32_t>(kBlockM / p.cn));
   if (rc != PE_OK) return rc;
-  rc = encode_f16_2d(&tb, w, static_cast<uint64_t>(n), static_cast<uint64_t>(k), static_cast<uint32_t>(p.block_n));
+  rc = encode_f16_2d(&tb, w, static_cast<uint64_t>(n), static_cast<uint64_t>(k), static_cast<uint32_t>(p.block_n / p.cm));
   if (rc != PE_OK) return rc;
 
   switch (epilogue) {

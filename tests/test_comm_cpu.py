@@ -63,7 +63,7 @@ def _pipeline_worker(rank, world, port, n_ubatch, out_q):
                     stage.enqueue_tensor(torch.full((2, 3), float(i)))
                 assert done.wait(60), "results did not arrive"
                 stage.check_workers()
-            ctx.cmd_broadcast(0)
+                ctx.cmd_broadcast(0)   # as runtime.py: stop is broadcast before the stage context exits
             out_q.put(('results', [r.tolist() for r in results], hook_log))
         else:
             def work(payload):
