@@ -59,6 +59,13 @@ uint64_t pe_launch_count(void);
 int pe_layernorm(const void* x, const void* gamma, const void* beta, float eps, void* out_f32, void* out_f16,
                  int rows, int hidden, void* stream);
 
+/* Same with the residual add folded in: t = y + resid; sum_out (f32, may be NULL, may alias resid) = t;
+ * outputs = LayerNorm(t). Replaces `data += skip` + `layernorm_after` (`vit.py:62-66`), the `+ input_tensor`
+ * inside `ViTOutput` followed by the next block's `layernorm_before`, and `LayerNorm(dense + input)` in
+ * `BertSelfOutput` / `BertOutput`. */
+int pe_residual_layernorm(const void* y, const void* resid, const void* gamma, const void* beta, float eps,
+                          void* sum_out, void* out_f32, void* out_f16, int rows, int hidden, void* stream);
+
 /* ---- Dense contraction `out = epilogue(A @ W^T + bias)` on tcgen05 tensor cores ---------------
  * Replaces every `nn.Linear` on the path (`ViTSelfAttention.query/key/value`, `ViTSelfOutput.dense`,
  * `ViTIntermediate.dense`, `ViTOutput.dense` and the Bert equivalents; reference call sites
@@ -194,6 +201,10 @@ int pe_bert_embed(const void* ids, const void* pos_ids, const void* word, const 
  * localise a failure to the tcgen05 kernel; never selected by the product path. */
 int pe_debug_linear_simt(const void* a, const void* w, const void* bias, const void* resid, void* out, int m, int n,
                          int k, int epilogue, void* stream);
+
+/* While `buf` (device, >= 12 * 8 * grid bytes) is set, every pe_linear launch stores a per-CTA clock64 timeline
+ * (start, setup done, first operands landed, last MMA issued, accumulator ready, epilogue done, exit). */
+int pe_debug_gemm_trace(void* buf);
 
 #ifdef __cplusplus
 }

@@ -38,6 +38,7 @@ SYMBOLS = {
     'pe_last_error': (c_char_p, []),
     'pe_launch_count': (c_uint64, []),
     'pe_layernorm': (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    'pe_residual_layernorm': (c_int, [c_void_p] * 4 + [c_float] + [c_void_p] * 3 + [c_int, c_int, c_void_p]),
     'pe_linear': (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
     'pe_attention': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'pe_cast_f32_to_f16': (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -56,6 +57,7 @@ SYMBOLS = {
     'pe_stage_kernel_count': (c_int, [c_void_p]),
     'pe_patch_embed': (c_int, [c_void_p] * 7 + [c_int] * 6 + [c_void_p]),
     'pe_bert_embed': (c_int, [c_void_p] * 7 + [c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'pe_debug_gemm_trace': (c_int, [c_void_p]),
     'pe_debug_linear_simt': (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
 }
 

@@ -54,8 +54,8 @@ int linear_impl(const void* a, const void* w, const void* bias, const void* resi
                 cudaStream_t stream);
 int linear_simt_impl(const void* a, const void* w, const void* bias, const void* resid, void* out, int m, int n, int k,
                      int epilogue, cudaStream_t stream);
-int layernorm_impl(const void* x, const void* gamma, const void* beta, float eps, void* out_f32, void* out_f16,
-                   int rows, int hidden, cudaStream_t stream);
+int layernorm_impl(const void* x, const void* resid, const void* gamma, const void* beta, float eps, void* sum_out,
+                   void* out_f32, void* out_f16, int rows, int hidden, cudaStream_t stream);
 int attention_impl(const void* qkv, void* ctx, int batch, int tokens, int heads, int head_dim, cudaStream_t stream);
 int cast_impl(const void* src, void* dst, size_t n, bool to_half, cudaStream_t stream);
 size_t quant_words(size_t n, int bit);
@@ -67,6 +67,7 @@ int quant_stats_impl(const void* x, int items, size_t n, int bit, int clamp, voi
 int quant_decode_impl(const void* codes, int items, size_t n, int bit, const void* scale, const void* shift, void* out,
                       cudaStream_t stream);
 float clamp_factor(int bit, int gelu);
+void set_gemm_trace(void* buf);
 
 }  // namespace pe
 
@@ -80,7 +81,16 @@ int pe_layernorm(const void* x, const void* gamma, const void* beta, float eps, 
                  int hidden, void* stream) {
   int rc = pe::require_sm100();
   if (rc != PE_OK) return rc;
-  return pe::layernorm_impl(x, gamma, beta, eps, out_f32, out_f16, rows, hidden, static_cast<cudaStream_t>(stream));
+  return pe::layernorm_impl(x, nullptr, gamma, beta, eps, nullptr, out_f32, out_f16, rows, hidden,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int pe_residual_layernorm(const void* y, const void* resid, const void* gamma, const void* beta, float eps,
+                          void* sum_out, void* out_f32, void* out_f16, int rows, int hidden, void* stream) {
+  int rc = pe::require_sm100();
+  if (rc != PE_OK) return rc;
+  return pe::layernorm_impl(y, resid, gamma, beta, eps, sum_out, out_f32, out_f16, rows, hidden,
+                            static_cast<cudaStream_t>(stream));
 }
 
 int pe_linear(const void* a, const void* w, const void* bias, const void* resid, void* out, int m, int n, int k,
@@ -93,6 +103,11 @@ int pe_debug_linear_simt(const void* a, const void* w, const void* bias, const v
   int rc = pe::require_sm100();
   if (rc != PE_OK) return rc;
   return pe::linear_simt_impl(a, w, bias, resid, out, m, n, k, epilogue, static_cast<cudaStream_t>(stream));
+}
+
+int pe_debug_gemm_trace(void* buf) {
+  pe::set_gemm_trace(buf);
+  return PE_OK;
 }
 
 int pe_attention(const void* qkv, void* ctx, int batch, int tokens, int heads, int head_dim, void* stream) {

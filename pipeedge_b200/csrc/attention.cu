@@ -1,8 +1,11 @@
 // Unmasked multi-head self-attention, softmax(Q K^T * d^-0.5) V, for S <= ~700 tokens and d = 64.
-// One CTA per (64-query block, head, item): K and V of the head are staged once in shared memory
-// (cp.async, 16-byte chunks, padded rows -> conflict-free ldmatrix), each of the 4 warps owns 16 query
-// rows and walks the keys in chunks of 64 with an online softmax (fp32 max/sum, exp2 with the scale
-// folded in), P is rounded to fp16 for the P.V product, accumulators stay fp32 in registers.
+// One CTA per (query split, head, item): K and V of the head are staged once in shared memory with cp.async
+// (16-byte chunks, padded rows -> conflict-free ldmatrix, one commit group per 64-key chunk so that the first
+// chunk's maths overlaps the rest of the load); each warp owns 16 query rows and walks the keys in chunks of
+// 64 - the last chunk trimmed to whole 16-key groups - with an online softmax (fp32 max/sum, exp2 with the
+// scale folded in); P is rounded to fp16 for the P.V product, accumulators stay fp32 in registers. The number
+// of warps per CTA and of query splits is picked so that S = 197 wastes < 6 % of the rows (13 row groups ->
+// 2 CTAs of 7 warps) instead of padding to 256.
 // Round-1 version on the warp-level tensor-core path (mma.sync m16n8k16); attention is ~4% of the
 // block's FLOPs. Replaces HF eager_attention_forward (see pe_attention in the header).
 #include "../../include/pipeedge_b200.h"
@@ -13,15 +16,27 @@ namespace pe {
 void count_launches(int n);
 
 constexpr int kAttnD = 64;
-constexpr int kAttnQ = 64;
 constexpr int kAttnKc = 64;
 constexpr int kAttnLd = kAttnD + 8;  // halves per smem row (144 bytes)
-constexpr int kAttnThreads = 128;
+constexpr int kAttnMaxWarps = 8;
 
 __device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most `pending` of this thread's commit groups are still in flight
+__device__ __forceinline__ void cp_async_wait_pending(int pending) {
+  switch (pending) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+    case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+    case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+  }
+}
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -44,86 +59,99 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-__global__ void __launch_bounds__(kAttnThreads)
+// grid = (query splits, heads, items); block = warps * 32; each warp: 16 query rows.
+__global__ void __launch_bounds__(kAttnMaxWarps * 32)
 attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ ctx, int tokens, int heads, float scale_log2e) {
   extern __shared__ __align__(16) uint8_t attn_smem[];
-  const int spad = (tokens + kAttnKc - 1) / kAttnKc * kAttnKc;
+  const int nwarps = blockDim.x >> 5;
+  const int qrows = nwarps * 16;                          // query rows of this CTA
+  const int kpad = (tokens + 15) & ~15;                   // keys rounded up to whole 16-key groups
   __half* sq = reinterpret_cast<__half*>(attn_smem);
-  __half* sk = sq + kAttnQ * kAttnLd;
-  __half* sv = sk + static_cast<size_t>(spad) * kAttnLd;
+  __half* sk = sq + qrows * kAttnLd;
+  __half* sv = sk + static_cast<size_t>(kpad) * kAttnLd;
 
-  const int q0 = blockIdx.x * kAttnQ;
+  const int q0 = blockIdx.x * qrows;
   const int head = blockIdx.y;
   const int item = blockIdx.z;
   const int hidden = heads * kAttnD;
   const size_t row_pitch = static_cast<size_t>(3) * hidden;
   const __half* base = qkv + static_cast<size_t>(item) * tokens * row_pitch + static_cast<size_t>(head) * kAttnD;
   const int tid = threadIdx.x;
+  const int nchunks = (kpad + kAttnKc - 1) / kAttnKc;
 
-  // ---- stage Q block, K, V (rows past `tokens` are zero-filled)
+  // ---- stage Q (group 0 together with the first key chunk), then K/V chunk by chunk
   {
-    const int chunk = tid & 7;       // 16-byte chunk within the 128-byte head row
-    const int r0 = tid >> 3;         // 0..15
+    const int chunk16 = tid & 7;     // 16-byte chunk within the 128-byte head row
+    const int r0 = tid >> 3;
+    const int rstep = blockDim.x >> 3;
     const uint4 zero = make_uint4(0, 0, 0, 0);
-    for (int r = r0; r < kAttnQ; r += kAttnThreads / 8) {
-      __half* dst = sq + r * kAttnLd + chunk * 8;
-      if (q0 + r < tokens) cp_async_16(dst, base + static_cast<size_t>(q0 + r) * row_pitch + chunk * 8);
+    for (int r = r0; r < qrows; r += rstep) {
+      __half* dst = sq + r * kAttnLd + chunk16 * 8;
+      if (q0 + r < tokens) cp_async_16(dst, base + static_cast<size_t>(q0 + r) * row_pitch + chunk16 * 8);
       else *reinterpret_cast<uint4*>(dst) = zero;
     }
-    for (int r = r0; r < spad; r += kAttnThreads / 8) {
-      __half* dk = sk + static_cast<size_t>(r) * kAttnLd + chunk * 8;
-      __half* dv = sv + static_cast<size_t>(r) * kAttnLd + chunk * 8;
-      if (r < tokens) {
-        const __half* src = base + static_cast<size_t>(r) * row_pitch + chunk * 8;
-        cp_async_16(dk, src + hidden);
-        cp_async_16(dv, src + 2 * hidden);
-      } else {
-        *reinterpret_cast<uint4*>(dk) = zero;
-        *reinterpret_cast<uint4*>(dv) = zero;
+    for (int c = 0; c < nchunks; ++c) {
+      const int kend = min(kpad, (c + 1) * kAttnKc);
+      for (int r = c * kAttnKc + r0; r < kend; r += rstep) {
+        __half* dk = sk + static_cast<size_t>(r) * kAttnLd + chunk16 * 8;
+        __half* dv = sv + static_cast<size_t>(r) * kAttnLd + chunk16 * 8;
+        if (r < tokens) {
+          const __half* src = base + static_cast<size_t>(r) * row_pitch + chunk16 * 8;
+          cp_async_16(dk, src + hidden);
+          cp_async_16(dv, src + 2 * hidden);
+        } else {
+          *reinterpret_cast<uint4*>(dk) = zero;
+          *reinterpret_cast<uint4*>(dv) = zero;
+        }
       }
+      cp_async_commit();
     }
-    cp_async_wait_all();
-    __syncthreads();
   }
 
   const int warp = tid >> 5, lane = tid & 31;
-  const int wrow = warp * 16;  // this warp's first query row within the block
+  const int wrow = warp * 16;  // this warp's first query row within the CTA
+  const bool warp_active = q0 + wrow < tokens;   // warp-uniform; idle warps still take part in the barriers
 
-  // Q fragments for the 4 k-steps over d
   uint32_t qf[kAttnD / 16][4];
-#pragma unroll
-  for (int ks = 0; ks < kAttnD / 16; ++ks) {
-    const int r = wrow + (lane & 7) + ((lane >> 3) & 1) * 8;
-    const int c = ks * 16 + (lane >> 4) * 8;
-    ldmatrix_x4(qf[ks], sq + r * kAttnLd + c);
-  }
-
   float o[kAttnD / 8][4];
 #pragma unroll
   for (int i = 0; i < kAttnD / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
   float m_run[2] = {-INFINITY, -INFINITY};  // running max (of raw scores) for rows lane/4 and lane/4+8
   float l_run[2] = {0.f, 0.f};
 
-  const int nchunks = spad / kAttnKc;
   for (int kc = 0; kc < nchunks; ++kc) {
+    cp_async_wait_pending(nchunks - 1 - kc);
+    __syncthreads();
+    if (!warp_active) continue;
+    if (kc == 0) {
+#pragma unroll
+      for (int ks = 0; ks < kAttnD / 16; ++ks) {
+        const int r = wrow + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int c = ks * 16 + (lane >> 4) * 8;
+        ldmatrix_x4(qf[ks], sq + r * kAttnLd + c);
+      }
+    }
     const int key0 = kc * kAttnKc;
+    const int ngrp = min(kAttnKc, kpad - key0) >> 4;   // 16-key groups in this chunk (1..4), warp-uniform
     float s[kAttnKc / 8][4];
 #pragma unroll
     for (int i = 0; i < kAttnKc / 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
-    // S = Q K^T for 64 keys
+    // S = Q K^T
 #pragma unroll
     for (int ks = 0; ks < kAttnD / 16; ++ks) {
 #pragma unroll
       for (int np = 0; np < kAttnKc / 16; ++np) {
-        uint32_t kf[4];
-        const int key = key0 + np * 16 + (lane & 7) + (lane >> 4) * 8;
-        const int c = ks * 16 + ((lane >> 3) & 1) * 8;
-        ldmatrix_x4(kf, sk + static_cast<size_t>(key) * kAttnLd + c);
-        mma_16816(s[2 * np], qf[ks], kf[0], kf[1]);
-        mma_16816(s[2 * np + 1], qf[ks], kf[2], kf[3]);
+        if (np < ngrp) {
+          uint32_t kf[4];
+          const int key = key0 + np * 16 + (lane & 7) + (lane >> 4) * 8;
+          const int c = ks * 16 + ((lane >> 3) & 1) * 8;
+          ldmatrix_x4(kf, sk + static_cast<size_t>(key) * kAttnLd + c);
+          mma_16816(s[2 * np], qf[ks], kf[0], kf[1]);
+          mma_16816(s[2 * np + 1], qf[ks], kf[2], kf[3]);
+        }
       }
     }
-    // mask keys past the sequence end (only possible in the last chunk)
+    // mask keys past the sequence end (also the groups this chunk does not have)
     if (key0 + kAttnKc > tokens) {
 #pragma unroll
       for (int nt = 0; nt < kAttnKc / 8; ++nt) {
@@ -147,7 +175,7 @@ attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ ctx, int t
     float corr[2], msc[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const float m_new = fmaxf(m_run[h], mx[h]);   // chunk 0 always holds a real key -> finite
+      const float m_new = fmaxf(m_run[h], mx[h]);   // every chunk holds at least one real key -> finite
       corr[h] = exp2f((m_run[h] - m_new) * scale_log2e);
       m_run[h] = m_new;
       msc[h] = m_new * scale_log2e;
@@ -180,17 +208,20 @@ attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ ctx, int t
     // O += P V
 #pragma unroll
     for (int ks = 0; ks < kAttnKc / 16; ++ks) {
+      if (ks < ngrp) {
 #pragma unroll
-      for (int dp = 0; dp < kAttnD / 16; ++dp) {
-        uint32_t vf[4];
-        const int key = key0 + ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-        const int c = dp * 16 + (lane >> 4) * 8;
-        ldmatrix_x4_trans(vf, sv + static_cast<size_t>(key) * kAttnLd + c);
-        mma_16816(o[2 * dp], pf[ks], vf[0], vf[1]);
-        mma_16816(o[2 * dp + 1], pf[ks], vf[2], vf[3]);
+        for (int dp = 0; dp < kAttnD / 16; ++dp) {
+          uint32_t vf[4];
+          const int key = key0 + ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+          const int c = dp * 16 + (lane >> 4) * 8;
+          ldmatrix_x4_trans(vf, sv + static_cast<size_t>(key) * kAttnLd + c);
+          mma_16816(o[2 * dp], pf[ks], vf[0], vf[1]);
+          mma_16816(o[2 * dp + 1], pf[ks], vf[2], vf[3]);
+        }
       }
     }
   }
+  if (!warp_active) return;
 
   // ---- normalise and store the merged-head context
   const float inv0 = 1.0f / l_run[0], inv1 = 1.0f / l_run[1];
@@ -210,18 +241,28 @@ int attention_impl(const void* qkv, void* ctx, int batch, int tokens, int heads,
   PE_REQUIRE(qkv && ctx, "pe_attention: null pointer");
   PE_REQUIRE(head_dim == kAttnD, "pe_attention: head_dim=%d unsupported (only 64)", head_dim);
   PE_REQUIRE(batch > 0 && tokens > 0 && heads > 0, "pe_attention: bad shape");
-  const int spad = (tokens + kAttnKc - 1) / kAttnKc * kAttnKc;
-  const size_t smem = static_cast<size_t>(kAttnQ + 2 * spad) * kAttnLd * sizeof(__half);
+  // 16-row groups -> query splits of at most 8 warps; prefer the fewest splits (K/V are staged once per CTA)
+  // that still give the 148 SMs a full wave of CTAs
+  const int groups = (tokens + 15) / 16;
+  int splits = (groups + kAttnMaxWarps - 1) / kAttnMaxWarps;
+  while (static_cast<long>(splits) * heads * batch < kNumSMs && splits < groups) ++splits;
+  const int warps = (groups + splits - 1) / splits;
+  splits = (groups + warps - 1) / warps;
+  const int kpad = (tokens + 15) & ~15;
+  PE_REQUIRE((kpad + kAttnKc - 1) / kAttnKc <= 8, "pe_attention: tokens=%d exceeds 512", tokens);
+  const size_t smem = static_cast<size_t>(warps * 16 + 2 * kpad) * kAttnLd * sizeof(__half);
   PE_REQUIRE(smem <= 227 * 1024, "pe_attention: tokens=%d exceeds the shared-memory resident K/V limit", tokens);
   static size_t configured = 0;
+  if (configured == 0)
+    cudaFuncSetAttribute(attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (smem > configured) {
     PE_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
   }
-  const dim3 grid((tokens + kAttnQ - 1) / kAttnQ, heads, batch);
+  const dim3 grid(splits, heads, batch);
   const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
-  attention_kernel<<<grid, kAttnThreads, smem, stream>>>(static_cast<const __half*>(qkv), static_cast<__half*>(ctx),
-                                                         tokens, heads, scale_log2e);
+  attention_kernel<<<grid, warps * 32, smem, stream>>>(static_cast<const __half*>(qkv), static_cast<__half*>(ctx),
+                                                      tokens, heads, scale_log2e);
   PE_CUDA(cudaGetLastError());
   count_launches(1);
   return PE_OK;

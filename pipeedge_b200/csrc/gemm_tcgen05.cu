@@ -1,14 +1,16 @@
 // out = epilogue(A @ W^T + bias) on sm_100a tensor cores.
 //
 // One persistent CTA per SM, warp-specialised (Blackwell GEMM anatomy):
-//   warp 0      TMA producer: cp.async.bulk.tensor 2D boxes of A [128 x 64] and W [BN x 64] fp16 into a
+//   warp 16     TMA producer: cp.async.bulk.tensor 2D boxes of A [128 x 64] and W [BN x 64] fp16 into a
 //               ring of 128B-swizzled shared-memory stages, completion on `full` mbarriers
-//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per stage, accumulating
+//   warp 17     MMA issuer: one thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per stage, accumulating
 //               in TMEM; tcgen05.commit releases the stage (`empty`) and, after the last K block,
 //               publishes the accumulator (`tmem_full`)
-//   warps 2..9  epilogue: tcgen05.ld the 128 x BN fp32 accumulator out of TMEM (each warp owns a
+//   warps 0..15 epilogue: tcgen05.ld the 128 x BN fp32 accumulator out of TMEM (each warp owns a
 //               32-lane quarter and half of the columns), apply bias / GELU / residual, store to HBM,
 //               then hand the accumulator back (`tmem_empty`)
+// The two single-thread roles get the HIGHEST warp ids: the warp scheduler favours higher ids, and with the
+// roles on warps 0/1 the waiting epilogue warps starved them (r01a: ~650 cycles per K block whatever the tile).
 // Two accumulator stages (2 x 256 TMEM columns) let the epilogue of tile i overlap the MMAs of tile i+1.
 //
 // These GEMMs (M = 1.5k..6k tokens, N, K <= 4k) are L2-bandwidth bound with one 128 x BN tile per CTA: every
@@ -17,7 +19,7 @@
 // it and TMA-MULTICAST it to the others, likewise the CN CTAs sharing an A tile, cutting L2 reads by up to
 // CM (W) and CN (A). Every CTA's `full` barrier sees the bytes of its whole stage whoever issued them; a
 // stage is released to all of its writers at once (tcgen05.commit multicast onto their `empty` barriers).
-// CM, CN and BN (a runtime multiple of 16 in [16, 256]) are chosen per problem by a small cost model:
+// CM, CN and BN (a runtime multiple of 32 in [32, 256]) are chosen per problem by a small cost model:
 // waves x max(tensor time, L2 time).
 //
 // Replaces every nn.Linear on the reference path (see include/pipeedge_b200.h: pe_linear).
@@ -38,10 +40,12 @@ constexpr int kBlockK = 64;  // 64 fp16 = 128 bytes = one SWIZZLE_128B row
 constexpr int kUmmaK = 16;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
-constexpr int kNumEpiWarps = 8;
+constexpr int kNumEpiWarps = 16;   // 4 TMEM lane quarters x 4 column groups: the epilogue is issue-latency bound
 constexpr int kGemmThreads = (2 + kNumEpiWarps) * 32;
+constexpr int kProducerWarp = kNumEpiWarps;      // warp 16
+constexpr int kMmaWarp = kNumEpiWarps + 1;       // warp 17
 constexpr int kMaxStages = 8;
-constexpr int kPipeSmemBudget = 200 * 1024;
+constexpr int kPipeSmemBudget = 144 * 1024;   // operand ring; the epilogue staging (80 KiB) follows it
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
 
 struct GemmParams {
@@ -52,6 +56,9 @@ struct GemmParams {
   int block_n;
   int stages;
   int num_m_blocks, num_n_blocks, num_k_blocks;
+  long long* trace;                // debug: per-CTA clock64 timeline (8 slots) or nullptr
+  int tma_store;                   // 1: epilogue stages 32-row boxes in swizzled smem and TMA-stores them
+  int debug_mode;                  // debug (wrong results!): 1 = skip MMAs, 2 = skip TMA loads, 3 = skip the A loads
   int cm, cn;                      // cluster shape: CM CTAs along M share a W tile, CN along N share an A tile
   int num_super_m, num_super_n;    // cluster-level tiles (CM*128 x CN*BN)
   // Optional output-row remap (patch embedding writes token rows 1.. of each item and adds a
@@ -63,72 +70,138 @@ struct GemmParams {
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// GELU with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 on erf, far below the fp16 rounding of the value
+// this feeds), arranged for the epilogue's instruction budget: ~12 FP32 ops + 2 MUFU (rcp.approx, ex2.approx) per
+// element instead of erff's ~40 - the FC1 epilogue is issue bound (128 x 256 elements per CTA).
+//   gelu(x) = 0.5 x (1 + erf(x/sqrt2)) = 0.5 (x + |x| (1 - q)),  q = t (a1 + t (a2 + ...)) exp(-x^2/2), t = 1/(1 + p|x|/sqrt2)
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float ax = fabsf(x);
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752f, ax, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170f));   // exp(-x^2 / 2)
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float q = poly * t * e;
+  return 0.5f * fmaf(ax, 1.0f - q, x);
+}
 
-template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int col0, const uint32_t (&r)[16]) {
-  int out_row = row, resid_row = row;
+constexpr int kStgLd = 36;                        // floats per staged row: 144 B keeps 16-byte accesses conflict-free
+constexpr int kStgFloatsPerWarp = 1280;           // 5 KiB per epilogue warp: a 32 x 36 fp32 chunk, or a 1 KiB-aligned 4 KiB TMA box
+constexpr int kStgBytes = kNumEpiWarps * kStgFloatsPerWarp * 4;
+
+__device__ __forceinline__ void map_rows(const GemmParams& p, int row, int& out_row, int& resid_row) {
+  out_row = row;
+  resid_row = row;
   if (p.rows_per_item > 0) {
     const int item = row / p.rows_per_item;
     const int in_item = row - item * p.rows_per_item + p.out_row_offset;
     out_row = item * p.out_item_rows + in_item;
     resid_row = p.resid_per_item ? in_item : out_row;
   }
-  float v[16];
+}
+
+template <int EPI>
+__device__ __forceinline__ float epi_act(float x) {
+  if (EPI == PE_EPI_GELU_F16) return gelu_erf_fast(x);
+  if (EPI == PE_EPI_TANH_F32) return tanhf(x);
+  return x;
+}
+
+// One 32-row x 32-column chunk of the accumulator, already staged row-major in `stg` (this warp's private
+// shared memory): re-read it so that consecutive lanes cover consecutive columns of a row, then apply the
+// epilogue and store. TMEM hands each lane one ROW (tcgen05.ld 32x32b), which would make every global access
+// touch 32 different lines (r01a: the epilogue took longer than the main loop); after the transpose each
+// instruction covers whole 64-128 byte row segments and the residual loads of a chunk are all in flight at once.
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk32(const GemmParams& p, const float* stg, int row0, int col0, int lane) {
+  constexpr bool kHalfOut = (EPI == PE_EPI_F16 || EPI == PE_EPI_GELU_F16);
+  const bool vec_ok = (p.n & 7) == 0;
+  if (kHalfOut) {
+    // lane -> (row = it*8 + lane/4, 8 columns starting at (lane%4)*8): 16-byte fp16 stores, 64 B per row
+    const int cc = (lane & 3) * 8;
+    const int col = col0 + cc;
+    const bool fast = vec_ok && col + 8 <= p.n;
+    float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+    if (p.bias != nullptr && fast) {   // this lane's 8 columns are the same for all of its rows
+      b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+      b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+    }
 #pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-  const bool full = (col0 + 16 <= p.n) && ((p.n & 7) == 0);
-  if (full) {
-    if (p.bias != nullptr) {
-      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+    for (int it = 0; it < 4; ++it) {
+      const int rr = it * 8 + (lane >> 2);
+      const int row = row0 + rr;
+      if (row >= p.m || col >= p.n) continue;
+      int out_row, resid_row;
+      map_rows(p, row, out_row, resid_row);
+      const float4 a = *reinterpret_cast<const float4*>(stg + rr * kStgLd + cc);
+      const float4 b = *reinterpret_cast<const float4*>(stg + rr * kStgLd + cc + 4);
+      float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      __half* o = reinterpret_cast<__half*>(p.out) + static_cast<size_t>(out_row) * p.n + col;
+      if (fast) {
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        uint4 pk;
+        __half2* h2 = reinterpret_cast<__half2*>(&pk);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 b = __ldg(b4 + i);
-        v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+        for (int i = 0; i < 4; ++i) h2[i] = __floats2half2_rn(epi_act<EPI>(v[2 * i]), epi_act<EPI>(v[2 * i + 1]));
+        *reinterpret_cast<uint4*>(o) = pk;
+      } else {
+        for (int i = 0; i < 8 && col + i < p.n; ++i) {
+          float x = v[i];
+          if (p.bias != nullptr) x += __ldg(p.bias + col + i);
+          o[i] = __float2half_rn(epi_act<EPI>(x));
+        }
       }
-    }
-    if (EPI == PE_EPI_GELU_F16) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
-    }
-    if (EPI == PE_EPI_TANH_F32) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
-    }
-    if (EPI == PE_EPI_RESID_F32) {
-      const float4* r4 = reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(resid_row) * p.n + col0);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 b = r4[i];
-        v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-      }
-    }
-    if (EPI == PE_EPI_F16 || EPI == PE_EPI_GELU_F16) {
-      __half* o = reinterpret_cast<__half*>(p.out) + static_cast<size_t>(out_row) * p.n + col0;
-      uint4 pk[2];
-      __half2* h2 = reinterpret_cast<__half2*>(pk);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) h2[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-      reinterpret_cast<uint4*>(o)[0] = pk[0];
-      reinterpret_cast<uint4*>(o)[1] = pk[1];
-    } else {
-      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(out_row) * p.n + col0);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     }
   } else {
-    // ragged right edge or an N that breaks 16-byte alignment: guarded scalar path
-    for (int i = 0; i < 16; ++i) {
-      const int col = col0 + i;
-      if (col >= p.n) break;
-      float x = v[i];
-      if (p.bias != nullptr) x += __ldg(p.bias + col);
-      if (EPI == PE_EPI_GELU_F16) x = gelu_erf(x);
-      if (EPI == PE_EPI_TANH_F32) x = tanhf(x);
-      if (EPI == PE_EPI_RESID_F32) x += p.resid[static_cast<size_t>(resid_row) * p.n + col];
-      if (EPI == PE_EPI_F16 || EPI == PE_EPI_GELU_F16) {
-        reinterpret_cast<__half*>(p.out)[static_cast<size_t>(out_row) * p.n + col] = __float2half_rn(x);
+    // lane -> (row = it*4 + lane/8, 4 columns starting at (lane%8)*4): 16-byte fp32 accesses, 128 B per row
+    const int cc = (lane & 7) * 4;
+    const int col = col0 + cc;
+    const bool col_ok = col < p.n;
+    const bool fast = vec_ok && col + 4 <= p.n;
+    float4 res[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (EPI == PE_EPI_RESID_F32) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {   // all residual loads of the chunk are issued before any is used
+        const int row = row0 + it * 4 + (lane >> 3);
+        if (row < p.m && fast) {
+          int out_row, resid_row;
+          map_rows(p, row, out_row, resid_row);
+          res[it] = *reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(resid_row) * p.n + col);
+        }
+      }
+    }
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias != nullptr && fast) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + (lane >> 3);
+      const int row = row0 + rr;
+      if (row >= p.m || !col_ok) continue;
+      int out_row, resid_row;
+      map_rows(p, row, out_row, resid_row);
+      const float4 a = *reinterpret_cast<const float4*>(stg + rr * kStgLd + cc);
+      float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(out_row) * p.n + col;
+      if (fast) {
+        float4 r4;
+        r4.x = epi_act<EPI>(a.x + bias4.x) + res[it].x;
+        r4.y = epi_act<EPI>(a.y + bias4.y) + res[it].y;
+        r4.z = epi_act<EPI>(a.z + bias4.z) + res[it].z;
+        r4.w = epi_act<EPI>(a.w + bias4.w) + res[it].w;
+        *reinterpret_cast<float4*>(o) = r4;
       } else {
-        reinterpret_cast<float*>(p.out)[static_cast<size_t>(out_row) * p.n + col] = x;
+        const float v[4] = {a.x, a.y, a.z, a.w};
+        for (int i = 0; i < 4 && col + i < p.n; ++i) {
+          float x = v[i];
+          if (p.bias != nullptr) x += __ldg(p.bias + col + i);
+          x = epi_act<EPI>(x);
+          if (EPI == PE_EPI_RESID_F32) x += p.resid[static_cast<size_t>(resid_row) * p.n + col + i];
+          o[i] = x;
+        }
       }
     }
   }
@@ -137,7 +210,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
 template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                    const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tm_out, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -147,6 +220,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  long long* trace = p.trace != nullptr ? p.trace + static_cast<size_t>(blockIdx.x) * 12 : nullptr;
+  if (trace != nullptr && threadIdx.x == 0) trace[0] = clock64();
   // SWIZZLE_128B tiles must start on 1024-byte boundaries
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -162,7 +237,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   for (int m = 0; m < p.cm; ++m) col_mask |= static_cast<uint16_t>(1u << (m + p.cm * n_rank));
   const uint16_t peers_mask = row_mask | col_mask;   // everyone who writes into my stages == everyone I write into
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
     for (int s = 0; s < p.stages; ++s) {
@@ -175,7 +250,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     }
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tmem_alloc(&tmem_base_smem, kTmemCols);
     tmem_relinquish();
   }
@@ -184,108 +259,193 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   if (csize > 1) cluster_sync_all();   // peers must not multicast into barriers that are not initialised yet
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  if (trace != nullptr && threadIdx.x == 0) trace[1] = clock64();
   const int num_supers = p.num_super_m * p.num_super_n;
   const int cluster_id = static_cast<int>(blockIdx.x) / csize;
   const int num_clusters = static_cast<int>(gridDim.x) / csize;
   const int a_slice_rows = kBlockM / p.cn;       // my share of the A tile
   const int b_slice_rows = p.block_n / p.cm;     // my share of the W tile
 
-  if (warp == 0) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ TMA producer
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int sup = cluster_id; sup < num_supers; sup += num_clusters) {
-        const int m_blk = (sup % p.num_super_m) * p.cm + m_rank;
-        const int n_blk = (sup / p.num_super_m) * p.cn + n_rank;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);   // every CTA I multicast into has drained this stage
-          uint8_t* sa = smem_gen + static_cast<size_t>(stage) * stage_bytes;
-          mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-          uint8_t* a_dst = sa + static_cast<size_t>(n_rank) * a_slice_rows * (kBlockK * 2);
-          uint8_t* b_dst = sa + kABytes + static_cast<size_t>(m_rank) * b_slice_rows * (kBlockK * 2);
-          const int a_row = m_blk * kBlockM + n_rank * a_slice_rows;
-          const int b_row = n_blk * p.block_n + m_rank * b_slice_rows;
-          if (p.cn > 1) tma_load_2d_multicast(a_dst, &tm_a, &full_bar[stage], kb * kBlockK, a_row, row_mask);
-          else tma_load_2d(a_dst, &tm_a, &full_bar[stage], kb * kBlockK, a_row);
-          if (p.cm > 1) tma_load_2d_multicast(b_dst, &tm_b, &full_bar[stage], kb * kBlockK, b_row, col_mask);
-          else tma_load_2d(b_dst, &tm_b, &full_bar[stage], kb * kBlockK, b_row);
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+  const uint32_t full_addr0 = smem_u32(&full_bar[0]);
+  const uint32_t empty_addr0 = smem_u32(&empty_bar[0]);
+  const int num_k_blocks = p.num_k_blocks, num_stages = p.stages;
+  if (warp == kProducerWarp) {
+    // ---------------------------------------------------------------- TMA producer (warp converged, one lane issues)
+    const int cm = p.cm, cn = p.cn, nsm = p.num_super_m, bn = p.block_n;
+    const uint32_t a_off = static_cast<uint32_t>(n_rank * a_slice_rows) * (kBlockK * 2);
+    const uint32_t b_off = kABytes + static_cast<uint32_t>(m_rank * b_slice_rows) * (kBlockK * 2);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int sup = cluster_id; sup < num_supers; sup += num_clusters) {
+      const int a_row = ((sup % nsm) * cm + m_rank) * kBlockM + n_rank * a_slice_rows;
+      const int b_row = ((sup / nsm) * cn + n_rank) * bn + m_rank * b_slice_rows;
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        const uint32_t full_addr = full_addr0 + static_cast<uint32_t>(stage) * 8u;
+        mbar_wait_addr(empty_addr0 + static_cast<uint32_t>(stage) * 8u, phase ^ 1u);   // all my destinations drained it
+        if (elect_one()) {
+          const uint32_t sa = smem_base + static_cast<uint32_t>(stage) * stage_bytes;
+          mbar_arrive_expect_tx_addr(full_addr, stage_bytes);
+          if (cn > 1) tma_load_2d_multicast_addr(sa + a_off, &tm_a, full_addr, kb * kBlockK, a_row, row_mask);
+          else tma_load_2d_addr(sa + a_off, &tm_a, full_addr, kb * kBlockK, a_row);
+          if (cm > 1) tma_load_2d_multicast_addr(sa + b_off, &tm_b, full_addr, kb * kBlockK, b_row, col_mask);
+          else tma_load_2d_addr(sa + b_off, &tm_b, full_addr, kb * kBlockK, b_row);
         }
+        __syncwarp();
+        if (++stage == num_stages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ MMA issuer (single thread)
-      const uint32_t idesc = umma_idesc_f16(kBlockM, p.block_n);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int sup = cluster_id; sup < num_supers; sup += num_clusters) {
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+  } else if (warp == kMmaWarp) {
+    // ---------------------------------------------------------------- MMA issuer (warp converged, one lane issues)
+    const uint32_t idesc = umma_idesc_f16(kBlockM, p.block_n);
+    const uint32_t a_lo0 = umma_desc_lo(smem_base);
+    const uint32_t stage_lo = stage_bytes >> 4;
+    const uint32_t tmem_full_addr0 = smem_u32(&tmem_full_bar[0]);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int sup = cluster_id; sup < num_supers; sup += num_clusters) {
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccStride);
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        mbar_wait_addr(full_addr0 + static_cast<uint32_t>(stage) * 8u, phase);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccStride);
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tcgen05_fence_after();
-          const uint32_t a_addr = smem_base + static_cast<uint32_t>(stage) * stage_bytes;
-          const uint64_t desc_a = umma_desc_kmajor_sw128(a_addr);
-          const uint64_t desc_b = umma_desc_kmajor_sw128(a_addr + kABytes);
+        if (trace != nullptr && sup == cluster_id && kb == 0 && lane == 0) trace[2] = clock64();
+        if (elect_one()) {
+          const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(stage) * stage_lo;
+          const uint32_t b_lo = a_lo + (kABytes >> 4);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // advancing K by 16 fp16 = 32 bytes inside the swizzled row: +2 in 16-byte units
-            umma_f16_ss(d_tmem, desc_a + static_cast<uint64_t>(k * 2), desc_b + static_cast<uint64_t>(k * 2), idesc,
-                        (kb | k) != 0 ? 1u : 0u);
+            umma_f16_ss_lohi(d_tmem, a_lo + k * 2, b_lo + k * 2, kUmmaDescHiSw128, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           // release the stage to every CTA that wrote part of it (incl. this one)
-          if (csize > 1) umma_commit_multicast(&empty_bar[stage], peers_mask);
-          else umma_commit(&empty_bar[stage]);
-          if (kb == p.num_k_blocks - 1) umma_commit(&tmem_full_bar[acc]);
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          const uint32_t empty_addr = empty_addr0 + static_cast<uint32_t>(stage) * 8u;
+          if (csize > 1) umma_commit_multicast_addr(empty_addr, peers_mask);
+          else umma_commit_addr(empty_addr);
+          if (kb == num_k_blocks - 1) umma_commit_addr(tmem_full_addr0 + static_cast<uint32_t>(acc) * 8u);
         }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+        __syncwarp();
+        if (++stage == num_stages) { stage = 0; phase ^= 1u; }
       }
+      if (trace != nullptr && sup == cluster_id && lane == 0) trace[3] = clock64();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
     }
   } else {
     // -------------------------------------------------------------- epilogue warps
     const int quarter = warp & 3;          // TMEM lanes [32*quarter, 32*quarter+32) are this warp's
-    const int half = (warp - 2) >> 2;      // which half of the tile's 16-column chunks
-    const int chunks = p.block_n >> 4;
-    const int c_mid = (chunks + 1) >> 1;
-    const int c_begin = half == 0 ? 0 : c_mid;
-    const int c_end = half == 0 ? c_mid : chunks;
+    const int group = warp >> 2;           // 32-column chunks c = group, group + 4, ... are this warp's
+    const int chunks = p.block_n >> 5;     // block_n is a multiple of 32
+    float* stg = reinterpret_cast<float*>(smem_gen + static_cast<size_t>(p.stages) * stage_bytes) + warp * kStgFloatsPerWarp;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int sup = cluster_id; sup < num_supers; sup += num_clusters) {
       const int m_blk = (sup % p.num_super_m) * p.cm + m_rank;
       const int n_blk = (sup / p.num_super_m) * p.cn + n_rank;
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      mbar_wait_relaxed(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
-      const int row = m_blk * kBlockM + quarter * 32 + lane;
+      if (trace != nullptr && sup == cluster_id && warp == 0 && lane == 0) trace[4] = clock64();
+      const int row0 = m_blk * kBlockM + quarter * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(acc * kAccStride);
-      for (int c = c_begin; c < c_end; ++c) {
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>(c * 16), r);
+      if (p.tma_store) {
+        // ---- TMEM -> registers -> (bias, activation, convert) -> 128B-swizzled shared box -> TMA store.
+        // One box = this warp's 32 rows x 128 bytes (64 fp16 or 32 fp32 columns); TMA clips the M / N tails.
+        constexpr bool kHalfOut = (EPI == PE_EPI_F16 || EPI == PE_EPI_GELU_F16);
+        constexpr int kBoxCols = kHalfOut ? 64 : 32;
+        const int boxes = (p.block_n + kBoxCols - 1) / kBoxCols;
+        uint8_t* box = reinterpret_cast<uint8_t*>(stg);            // 4 KiB, 1024-byte aligned
+        const uint32_t box_addr = smem_u32(box);
+        uint8_t* my_row = box + lane * 128;
+        const int sw = lane & 7;                                   // 16-byte chunk j of row r lives at j ^ (r & 7)
+        for (int bx = group; bx < boxes; bx += kNumEpiWarps / 4) {
+          const int col0 = n_blk * p.block_n + bx * kBoxCols;
+          if (lane == 0) tma_store_wait_read();                    // the previous box has left shared memory
+          __syncwarp();
+#pragma unroll
+          for (int hseg = 0; hseg < kBoxCols / 32; ++hseg) {
+            const int cbase = bx * kBoxCols + hseg * 32;           // column within the tile
+            if (cbase >= p.block_n) break;
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(cbase), r);
+            tmem_wait_ld();
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            const int gcol = n_blk * p.block_n + cbase;
+            if (p.bias != nullptr) {
+              if (gcol + 32 <= p.n) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol) + i);
+                  v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (gcol + i < p.n) v[i] += __ldg(p.bias + gcol + i);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = epi_act<EPI>(v[i]);
+            if (kHalfOut) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {                        // 4 chunks of 8 halves
+                uint4 pk;
+                __half2* h2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) h2[i] = __floats2half2_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
+                *reinterpret_cast<uint4*>(my_row + (((hseg * 4 + j) ^ sw) << 4)) = pk;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)                          // 8 chunks of 4 floats
+                *reinterpret_cast<float4*>(my_row + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+          }
+          fence_proxy_async_smem();                                // generic-proxy writes -> visible to the TMA engine
+          __syncwarp();
+          if (lane == 0 && row0 < p.m && col0 < p.n) {
+            tma_store_2d(&tm_out, box_addr, col0, row0);
+            tma_store_commit();
+          }
+        }
+      } else
+      for (int c = group; c < chunks; c += kNumEpiWarps / 4) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c * 32), r);
         tmem_wait_ld();
-        const int col0 = n_blk * p.block_n + c * 16;
-        if (row < p.m && col0 < p.n) epilogue_chunk<EPI>(p, row, col0, r);
+        if (trace != nullptr && sup == cluster_id && warp == 0 && lane == 0 && c == group) trace[7] = clock64();
+        float4* dst = reinterpret_cast<float4*>(stg + lane * kStgLd);   // lane = accumulator row
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                               __uint_as_float(r[4 * j + 3]));
+        __syncwarp();
+        if (trace != nullptr && sup == cluster_id && warp == 0 && lane == 0 && c == group) trace[8] = clock64();
+        const int col0 = n_blk * p.block_n + c * 32;
+        if (row0 < p.m && col0 < p.n) epilogue_chunk32<EPI>(p, stg, row0, col0, lane);
+        __syncwarp();
+        if (trace != nullptr && sup == cluster_id && warp == 0 && lane == 0 && c == group) trace[9] = clock64();
       }
       tcgen05_fence_before();
       __syncwarp();
+      if (trace != nullptr && sup == cluster_id && warp == 0 && lane == 0) trace[5] = clock64();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
   }
 
+  if (warp < kNumEpiWarps && lane == 0) tma_store_wait_all();
   tcgen05_fence_before();
   __syncthreads();
   // no CTA may leave while a peer can still multicast into its shared memory or arrive on its barriers
   if (csize > 1) cluster_sync_all();
-  if (warp == 1) {
+  if (trace != nullptr && threadIdx.x == 0) trace[6] = clock64();
+  if (warp == kMmaWarp) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -330,6 +490,27 @@ static int encode_f16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint6
   return PE_OK;
 }
 
+static long long* g_gemm_trace = nullptr;   // set by pe_debug_gemm_trace
+void set_gemm_trace(void* buf) { g_gemm_trace = static_cast<long long*>(buf); }
+
+// Output [rows, cols] (fp16 or fp32) -> boxes of [32 rows, 128 bytes] with the 128-byte swizzle for TMA stores.
+static int encode_out_2d(CUtensorMap* map, void* ptr, uint64_t rows, uint64_t cols, bool half_out) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return PE_ERR_CUDA;
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * (half_out ? 2u : 4u)};
+  const cuuint32_t box[2] = {half_out ? 64u : 32u, 32u};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult rc = fn(map, half_out ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims,
+                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (output) failed (CUresult %d)", static_cast<int>(rc));
+    return PE_ERR_CUDA;
+  }
+  return PE_OK;
+}
+
 struct GemmPlan {
   int cm, cn, bn;
 };
@@ -339,30 +520,37 @@ static int max_clusters(int csize) {
   return csize == 1 ? kNumSMs : (csize == 2 ? kNumSMs / 2 : 132 / csize);
 }
 
-// Cost model (SM cycles): waves x max(tensor time of one tile, L2->SM time of one wave's operand reads) + launch.
-// Tensor: 128 x BN x 16 MMA = BN/2 cycles. L2: ~3300 bytes per SM-cycle chip-wide (~6.4 TB/s), the rate the
-// r01a kernels saturated at. A cluster reads (CM*128 + CN*BN) * K * 2 bytes per cluster tile.
-GemmPlan plan_gemm(int m, int n, int k) {
+// Cost model in SM cycles, fitted to per-CTA clock64 timelines measured on B200 (profiles/r01b_gemm_timeline.txt):
+//   set-up ~1200 (+800 for a cluster launch) and ~2000 until the first operands land;
+//   main loop: K/64 blocks, each max(2*BN tensor cycles, ~450 issue/latency floor);
+//   earlier waves' epilogues hide under the next tile's main loop; the last wave's is exposed and is the larger
+//   of its store burst (~1400 B/cycle chip-wide, every CTA stores at once) and the per-warp chunk latency.
+// Clusters (TMA multicast) cut L2 reads, but these shapes are not L2-bound, so they rarely win.
+GemmPlan plan_gemm(int m, int n, int k, int out_elem_bytes) {
   int forced[3] = {0, 0, 0};
   const char* env = getenv("PE_GEMM_FORCE");   // "CM,CN,BN": tuning / debugging only
   if (env != nullptr && sscanf(env, "%d,%d,%d", &forced[0], &forced[1], &forced[2]) == 3 && forced[0] > 0)
     return {forced[0], forced[1], forced[2]};
-  GemmPlan best = {1, 1, 16};
+  GemmPlan best = {1, 1, 32};
   double best_cost = 1e30;
-  const int shapes[5][2] = {{1, 1}, {2, 1}, {1, 2}, {2, 2}, {4, 1}};
+  const int shapes[4][2] = {{1, 1}, {2, 1}, {1, 2}, {2, 2}};
+  const double kb = (k + kBlockK - 1) / kBlockK;
   for (const auto& sh : shapes) {
     const int cm = sh[0], cn = sh[1], csize = cm * cn;
-    for (int bn = 256; bn >= 16; bn -= 16) {
+    for (int bn = 256; bn >= 32; bn -= 32) {
       if ((bn / cm) % 8 != 0 || (bn % cm) != 0) continue;   // W slices must keep whole 8-row swizzle atoms
+      if (out_elem_bytes == 2 && (bn % 64) != 0) continue;  // fp16 TMA-store boxes are 64 columns wide
       const long sm_ = (m + kBlockM * cm - 1) / (kBlockM * cm);
       const long sn_ = (n + bn * cn - 1) / (bn * cn);
       const long supers = sm_ * sn_;
       const long avail = max_clusters(csize);
       const long waves = (supers + avail - 1) / avail;
-      const long active = supers < avail ? supers : avail;
-      const double tile_cycles = static_cast<double>(k) * bn / 32.0;
-      const double l2_cycles = static_cast<double>(cm * kBlockM + cn * bn) * k * 2.0 * active / 3300.0;
-      const double cost = waves * (tile_cycles > l2_cycles ? tile_cycles : l2_cycles) + 2500.0 + 150.0 * csize;
+      const double per_kb = 2.0 * bn > 450.0 ? 2.0 * bn : 450.0;
+      const double last_tiles = static_cast<double>(supers - (waves - 1) * avail) * csize;
+      const double burst = last_tiles * kBlockM * bn * out_elem_bytes / 1400.0;
+      const double lat = ((bn / 32 + 3) / 4) * (out_elem_bytes == 2 ? 1300.0 : 1500.0);
+      const double cost = 1200.0 + (csize > 1 ? 800.0 : 0.0) + 2000.0 + waves * kb * per_kb +
+                          (burst > lat ? burst : lat) + 500.0;
       if (cost < best_cost - 1e-9) {
         best_cost = cost;
         best = {cm, cn, bn};
@@ -373,16 +561,17 @@ GemmPlan plan_gemm(int m, int n, int k) {
 }
 
 template <int EPI>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmParams& p,
+                       cudaStream_t stream) {
   static bool configured = false;
   // the attribute bounds DYNAMIC shared memory; static barriers live outside it (227 KiB total per CTA)
-  const int max_smem = kPipeSmemBudget + 2048;
+  const int max_smem = kPipeSmemBudget + kStgBytes + 1024;
   if (!configured) {
     PE_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     configured = true;
   }
   const uint32_t stage_bytes = kABytes + static_cast<uint32_t>(p.block_n) * (kBlockK * 2);
-  const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + 1024;
+  const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + kStgBytes + 1024;
   const int csize = p.cm * p.cn;
   const int supers = p.num_super_m * p.num_super_n;
   const int avail = max_clusters(csize);
@@ -399,7 +588,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PE_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<EPI>, ta, tb, p));
+  PE_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<EPI>, ta, tb, tout, p));
   count_launches(1);
   return PE_OK;
 }
@@ -416,11 +605,12 @@ int linear_impl(const void* a, const void* w, const void* bias, const void* resi
   int rc = require_sm100();
   if (rc != PE_OK) return rc;
 
-  const GemmPlan plan = plan_gemm(m, n, k);
-  PE_REQUIRE(plan.bn >= 16 && plan.bn <= 256 && plan.bn % 16 == 0 && plan.cm >= 1 && plan.cn >= 1 &&
+  const GemmPlan plan = plan_gemm(m, n, k, (epilogue == PE_EPI_F16 || epilogue == PE_EPI_GELU_F16) ? 2 : 4);
+  PE_REQUIRE(plan.bn >= 32 && plan.bn <= 256 && plan.bn % 32 == 0 && plan.cm >= 1 && plan.cn >= 1 &&
                  plan.cm * plan.cn <= 8 && kBlockM % plan.cn == 0 && (plan.bn / plan.cm) % 8 == 0,
              "pe_linear: bad tile plan cm=%d cn=%d bn=%d", plan.cm, plan.cn, plan.bn);
   GemmParams p;
+  p.tma_store = 0;
   p.bias = static_cast<const float*>(bias);
   p.resid = static_cast<const float*>(resid);
   p.out = out;
@@ -436,6 +626,8 @@ int linear_impl(const void* a, const void* w, const void* bias, const void* resi
   p.num_k_blocks = (k + kBlockK - 1) / kBlockK;
   p.num_super_m = (p.num_m_blocks + p.cm - 1) / p.cm;
   p.num_super_n = (p.num_n_blocks + p.cn - 1) / p.cn;
+  p.trace = g_gemm_trace;
+  p.debug_mode = 0;
   p.rows_per_item = rows_per_item;
   p.out_item_rows = out_item_rows;
   p.out_row_offset = out_row_offset;
@@ -447,12 +639,24 @@ int linear_impl(const void* a, const void* w, const void* bias, const void* resi
   rc = encode_f16_2d(&tb, w, static_cast<uint64_t>(n), static_cast<uint64_t>(k), static_cast<uint32_t>(p.block_n / p.cm));
   if (rc != PE_OK) return rc;
 
+  // Output through TMA whenever the row pitch allows it; the residual / row-remapping epilogues keep per-thread stores.
+  const bool half_out = epilogue == PE_EPI_F16 || epilogue == PE_EPI_GELU_F16;
+  const size_t out_pitch = static_cast<size_t>(n) * (half_out ? 2 : 4);
+  CUtensorMap tout = ta;   // placeholder when unused
+  p.tma_store = (epilogue != PE_EPI_RESID_F32 && rows_per_item == 0 && (out_pitch & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
+  if (getenv("PE_GEMM_NO_TMA_STORE") != nullptr) p.tma_store = 0;
+  if (half_out && (p.block_n % 64) != 0) p.tma_store = 0;   // a box must not spill into the next tile's columns
+  if (p.tma_store) {
+    rc = encode_out_2d(&tout, out, static_cast<uint64_t>(m), static_cast<uint64_t>(n), half_out);
+    if (rc != PE_OK) return rc;
+  }
   switch (epilogue) {
-    case PE_EPI_F16: return launch_gemm<PE_EPI_F16>(ta, tb, p, stream);
-    case PE_EPI_GELU_F16: return launch_gemm<PE_EPI_GELU_F16>(ta, tb, p, stream);
-    case PE_EPI_RESID_F32: return launch_gemm<PE_EPI_RESID_F32>(ta, tb, p, stream);
-    case PE_EPI_F32: return launch_gemm<PE_EPI_F32>(ta, tb, p, stream);
-    case PE_EPI_TANH_F32: return launch_gemm<PE_EPI_TANH_F32>(ta, tb, p, stream);
+    case PE_EPI_F16: return launch_gemm<PE_EPI_F16>(ta, tb, tout, p, stream);
+    case PE_EPI_GELU_F16: return launch_gemm<PE_EPI_GELU_F16>(ta, tb, tout, p, stream);
+    case PE_EPI_RESID_F32: return launch_gemm<PE_EPI_RESID_F32>(ta, tb, tout, p, stream);
+    case PE_EPI_F32: return launch_gemm<PE_EPI_F32>(ta, tb, tout, p, stream);
+    case PE_EPI_TANH_F32: return launch_gemm<PE_EPI_TANH_F32>(ta, tb, tout, p, stream);
     default: set_error("pe_linear: unknown epilogue %d", epilogue); return PE_ERR_INVALID;
   }
 }

@@ -8,17 +8,29 @@ namespace pe {
 
 void count_launches(int n);
 
+// Every kernel of the stage asks for the same (maximum-shared) L1/shared split as the GEMM and attention kernels:
+// switching the carve-out between consecutive kernels makes the SMs drain and reconfigure.
+template <typename K>
+static void prefer_max_shared(K kernel) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 constexpr int kLnMaxVec = 12;  // float4 per lane: hidden <= 12 * 4 * 32 = 1536
 constexpr int kLnWarpsPerBlock = 4;
 
+// t = x (+ resid); optionally sum_out = t (the updated fp32 residual stream); then LayerNorm(t).
+// Folding the residual add in here keeps it out of the GEMM epilogues, where each lane owns a different ROW
+// and a residual read costs 32 cache lines per instruction; here a warp reads whole rows.
 __global__ void __launch_bounds__(kLnWarpsPerBlock * 32)
-layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 float eps, float* out_f32, __half* out_f16, int rows, int hidden) {
+layernorm_kernel(const float* __restrict__ x, const float* resid, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, float* sum_out, float* out_f32, __half* out_f16, int rows,
+                 int hidden) {
   const int row = blockIdx.x * kLnWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const int nvec = hidden >> 2;  // hidden % 4 == 0 enforced by the host
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * hidden);
+  const float4* rr = resid != nullptr ? reinterpret_cast<const float4*>(resid + static_cast<size_t>(row) * hidden) : nullptr;
   float4 v[kLnMaxVec];
   float sum = 0.f;
 #pragma unroll
@@ -26,6 +38,11 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
     const int idx = lane + i * 32;
     if (idx < nvec) {
       v[i] = xr[idx];
+      if (rr != nullptr) {
+        const float4 r = rr[idx];
+        v[i].x += r.x; v[i].y += r.y; v[i].z += r.z; v[i].w += r.w;
+        if (sum_out != nullptr) reinterpret_cast<float4*>(sum_out + static_cast<size_t>(row) * hidden)[idx] = v[i];
+      }
       sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
   }
@@ -64,15 +81,19 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
   }
 }
 
-int layernorm_impl(const void* x, const void* gamma, const void* beta, float eps, void* out_f32, void* out_f16,
-                   int rows, int hidden, cudaStream_t stream) {
+int layernorm_impl(const void* x, const void* resid, const void* gamma, const void* beta, float eps, void* sum_out,
+                   void* out_f32, void* out_f16, int rows, int hidden, cudaStream_t stream) {
   PE_REQUIRE(x && gamma && beta && (out_f32 || out_f16), "pe_layernorm: null pointer");
+  PE_REQUIRE(resid != nullptr || sum_out == nullptr, "pe_residual_layernorm: sum_out needs resid");
   PE_REQUIRE(rows > 0 && hidden > 0 && (hidden & 3) == 0 && hidden <= kLnMaxVec * 128,
              "pe_layernorm: hidden=%d must be a multiple of 4 and <= %d", hidden, kLnMaxVec * 128);
   const int grid = (rows + kLnWarpsPerBlock - 1) / kLnWarpsPerBlock;
+  static bool configured = false;
+  if (!configured) { prefer_max_shared(layernorm_kernel); configured = true; }
   layernorm_kernel<<<grid, kLnWarpsPerBlock * 32, 0, stream>>>(
-      static_cast<const float*>(x), static_cast<const float*>(gamma), static_cast<const float*>(beta), eps,
-      static_cast<float*>(out_f32), static_cast<__half*>(out_f16), rows, hidden);
+      static_cast<const float*>(x), static_cast<const float*>(resid), static_cast<const float*>(gamma),
+      static_cast<const float*>(beta), eps, static_cast<float*>(sum_out), static_cast<float*>(out_f32),
+      static_cast<__half*>(out_f16), rows, hidden);
   PE_CUDA(cudaGetLastError());
   count_launches(1);
   return PE_OK;
@@ -108,6 +129,8 @@ int cast_impl(const void* src, void* dst, size_t n, bool to_half, cudaStream_t s
   const int block = 256;
   size_t want = (n / 4 + block - 1) / block;
   const int grid = static_cast<int>(want < 1 ? 1 : (want > static_cast<size_t>(kNumSMs) * 8 ? kNumSMs * 8 : want));
+  static bool configured = false;
+  if (!configured) { prefer_max_shared(cast_f32_f16_kernel); prefer_max_shared(cast_f16_f32_kernel); configured = true; }
   if (to_half) {
     PE_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0,
                "pe_cast_f32_to_f16: misaligned");
@@ -117,6 +140,30 @@ int cast_impl(const void* src, void* dst, size_t n, bool to_half, cudaStream_t s
                "pe_cast_f16_to_f32: misaligned");
     cast_f16_f32_kernel<<<grid, block, 0, stream>>>(static_cast<const __half*>(src), static_cast<float*>(dst), n);
   }
+  PE_CUDA(cudaGetLastError());
+  count_launches(1);
+  return PE_OK;
+}
+
+// out = a + b (fp32): materialises the residual stream when a stage ends right after an output projection / FC2.
+__global__ void add_f32_kernel(const float* __restrict__ a, const float* b, float* out, size_t n4) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
+    const float4 x = reinterpret_cast<const float4*>(a)[i];
+    const float4 y = reinterpret_cast<const float4*>(b)[i];
+    reinterpret_cast<float4*>(out)[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+  }
+}
+
+int add_impl(const void* a, const void* b, void* out, size_t n, cudaStream_t stream) {
+  PE_REQUIRE(a && b && out && (n & 3) == 0, "pe_add: bad arguments");
+  const size_t n4 = n >> 2;
+  size_t want = (n4 + 255) / 256;
+  const int grid = static_cast<int>(want < 1 ? 1 : (want > static_cast<size_t>(kNumSMs) * 8 ? kNumSMs * 8 : want));
+  static bool configured = false;
+  if (!configured) { prefer_max_shared(add_f32_kernel); configured = true; }
+  add_f32_kernel<<<grid, 256, 0, stream>>>(static_cast<const float*>(a), static_cast<const float*>(b),
+                                           static_cast<float*>(out), n4);
   PE_CUDA(cudaGetLastError());
   count_launches(1);
   return PE_OK;

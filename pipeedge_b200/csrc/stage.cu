@@ -8,7 +8,8 @@
 //   qkv16             f16 [M, 3H]  [Q | K | V], head-major inside each third
 //   ctx16             f16 [M, H]   merged-head attention context = A operand of the output projection
 //   inter16           f16 [M, I]   GELU(FC1) = A operand of FC2
-//   t32               f32 [M, H]   BERT only: pre-LayerNorm sum
+//   t32               f32 [M, H]   output projection / FC2 result before the residual add, which is folded into
+//                                  the LayerNorm that follows (or a small add kernel when the stage ends there)
 // Replaces {ViT,DeiT,Bert}ModelShard.forward's block loop (vit.py:161-170, deit.py:158-167, bert.py:142-151).
 #include <map>
 #include <tuple>
@@ -24,8 +25,9 @@ int require_sm100();
 int linear_impl(const void* a, const void* w, const void* bias, const void* resid, void* out, int m, int n, int k,
                 int epilogue, int rows_per_item, int out_item_rows, int out_row_offset, int resid_per_item,
                 cudaStream_t stream);
-int layernorm_impl(const void* x, const void* gamma, const void* beta, float eps, void* out_f32, void* out_f16,
-                   int rows, int hidden, cudaStream_t stream);
+int layernorm_impl(const void* x, const void* resid, const void* gamma, const void* beta, float eps, void* sum_out,
+                   void* out_f32, void* out_f16, int rows, int hidden, cudaStream_t stream);
+int add_impl(const void* a, const void* b, void* out, size_t n, cudaStream_t stream);
 int attention_impl(const void* qkv, void* ctx, int batch, int tokens, int heads, int head_dim, cudaStream_t stream);
 int cast_impl(const void* src, void* dst, size_t n, bool to_half, cudaStream_t stream);
 int spin_impl(float ms, cudaStream_t stream);
@@ -109,8 +111,9 @@ static int enqueue(pe_stage* st, const void* in0, const void* in1, void* out0, v
 
   // every residual-stream write lands in the buffer that finally carries it out of the stage
   float* resid_dest = static_cast<float*>(out_tuple ? out1 : out0);
-  const float* x = nullptr;     // current fp32 residual stream
+  const float* x = nullptr;     // current fp32 residual stream, when materialised
   const float* skip = nullptr;  // skip tensor of a pending (data, skip) tuple
+  bool pending = false;         // residual stream = t32 + skip, not yet added (pre-LN only)
   bool a16_valid = false;       // a16 holds the f16 copy of x (post-LN only)
 
   if (first_sub == 0 || first_sub == 2) {
@@ -126,52 +129,54 @@ static int enqueue(pe_stage* st, const void* in0, const void* in1, void* out0, v
   for (const SubRange& r : st->ranges) {
     const pe_block_weights& w = st->blocks[r.block];
     for (int sub = r.s0; sub <= r.s1; ++sub) {
+      const bool attn_half = sub == 0;
       switch (sub) {
-        case 0: {
-          if (post_ln) {
-            if (!a16_valid) { PE_K(PE_KERNEL_CAST, cast_impl(x, st->a16, static_cast<size_t>(M) * H, true, stream)); }
-          } else {
-            PE_K(PE_KERNEL_LAYERNORM, layernorm_impl(x, w.ln1_w, w.ln1_b, d.eps, nullptr, st->a16, M, H, stream));
-          }
-          PE_K(PE_KERNEL_GEMM_QKV, lin(st->a16, w.w_qkv, w.b_qkv, nullptr, st->qkv16, M, 3 * H, H, PE_EPI_F16, stream));
-          PE_K(PE_KERNEL_ATTENTION, attention_impl(st->qkv16, st->ctx16, ubatch, S, d.heads, H / d.heads, stream));
-          skip = x; x = nullptr; a16_valid = false;
-          break;
-        }
-        case 1: {
-          if (post_ln) {
-            PE_K(PE_KERNEL_GEMM_OUT, lin(st->ctx16, w.w_o, w.b_o, skip, st->t32, M, H, H, PE_EPI_RESID_F32, stream));
-            PE_K(PE_KERNEL_LAYERNORM, layernorm_impl(st->t32, w.ln1_w, w.ln1_b, d.eps, resid_dest, st->a16, M, H, stream));
-            a16_valid = true;
-          } else {
-            PE_K(PE_KERNEL_GEMM_OUT, lin(st->ctx16, w.w_o, w.b_o, skip, resid_dest, M, H, H, PE_EPI_RESID_F32, stream));
-          }
-          x = resid_dest; skip = nullptr;
-          break;
-        }
+        case 0:
         case 2: {
+          const void* ln_w = attn_half ? w.ln1_w : w.ln2_w;
+          const void* ln_b = attn_half ? w.ln1_b : w.ln2_b;
           if (post_ln) {
             if (!a16_valid) { PE_K(PE_KERNEL_CAST, cast_impl(x, st->a16, static_cast<size_t>(M) * H, true, stream)); }
+          } else if (pending) {
+            // residual add of the previous sub-layer + this LayerNorm in one pass; the sum becomes the stream
+            PE_K(PE_KERNEL_LAYERNORM, layernorm_impl(st->t32, skip, ln_w, ln_b, d.eps, resid_dest, nullptr, st->a16, M, H, stream));
+            x = resid_dest;
+            pending = false;
           } else {
-            PE_K(PE_KERNEL_LAYERNORM, layernorm_impl(x, w.ln2_w, w.ln2_b, d.eps, nullptr, st->a16, M, H, stream));
+            PE_K(PE_KERNEL_LAYERNORM, layernorm_impl(x, nullptr, ln_w, ln_b, d.eps, nullptr, nullptr, st->a16, M, H, stream));
           }
-          PE_K(PE_KERNEL_GEMM_FC1, lin(st->a16, w.w_fc1, w.b_fc1, nullptr, st->inter16, M, I, H, PE_EPI_GELU_F16, stream));
+          if (attn_half) {
+            PE_K(PE_KERNEL_GEMM_QKV, lin(st->a16, w.w_qkv, w.b_qkv, nullptr, st->qkv16, M, 3 * H, H, PE_EPI_F16, stream));
+            PE_K(PE_KERNEL_ATTENTION, attention_impl(st->qkv16, st->ctx16, ubatch, S, d.heads, H / d.heads, stream));
+          } else {
+            PE_K(PE_KERNEL_GEMM_FC1, lin(st->a16, w.w_fc1, w.b_fc1, nullptr, st->inter16, M, I, H, PE_EPI_GELU_F16, stream));
+          }
           skip = x; x = nullptr; a16_valid = false;
           break;
         }
-        default: {
-          if (post_ln) {
-            PE_K(PE_KERNEL_GEMM_FC2, lin(st->inter16, w.w_fc2, w.b_fc2, skip, st->t32, M, H, I, PE_EPI_RESID_F32, stream));
-            PE_K(PE_KERNEL_LAYERNORM, layernorm_impl(st->t32, w.ln2_w, w.ln2_b, d.eps, resid_dest, st->a16, M, H, stream));
-            a16_valid = true;
+        default: {   // 1: output projection, 3: FC2 - both produce t32 = A @ W^T + b, residual add deferred
+          if (sub == 1) {
+            PE_K(PE_KERNEL_GEMM_OUT, lin(st->ctx16, w.w_o, w.b_o, nullptr, st->t32, M, H, H, PE_EPI_F32, stream));
           } else {
-            PE_K(PE_KERNEL_GEMM_FC2, lin(st->inter16, w.w_fc2, w.b_fc2, skip, resid_dest, M, H, I, PE_EPI_RESID_F32, stream));
+            PE_K(PE_KERNEL_GEMM_FC2, lin(st->inter16, w.w_fc2, w.b_fc2, nullptr, st->t32, M, H, I, PE_EPI_F32, stream));
           }
-          x = resid_dest; skip = nullptr;
+          if (post_ln) {
+            const void* ln_w = sub == 1 ? w.ln1_w : w.ln2_w;
+            const void* ln_b = sub == 1 ? w.ln1_b : w.ln2_b;
+            PE_K(PE_KERNEL_LAYERNORM, layernorm_impl(st->t32, skip, ln_w, ln_b, d.eps, nullptr, resid_dest, st->a16, M, H, stream));
+            a16_valid = true;
+            x = resid_dest; skip = nullptr;
+          } else {
+            pending = true;   // x = t32 + skip
+          }
           break;
         }
       }
     }
+  }
+  if (pending) {   // the stage ends on an output projection / FC2: materialise the sum
+    PE_K(PE_KERNEL_CAST, add_impl(st->t32, skip, resid_dest, static_cast<size_t>(M) * H, stream));
+    x = resid_dest; skip = nullptr; pending = false;
   }
 
   if (out_tuple) {

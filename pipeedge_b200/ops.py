@@ -41,6 +41,21 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return o32, o16
 
 
+def residual_layernorm(y: torch.Tensor, resid: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+                       want_sum: bool = True, want_f32: bool = False, want_f16: bool = True):
+    """t = y + resid; returns (t or None, LayerNorm(t) f32 or None, LayerNorm(t) f16 or None)."""
+    for name, t in (('y', y), ('resid', resid), ('gamma', gamma), ('beta', beta)):
+        _want(t, torch.float32, name)
+    hidden = y.shape[-1]
+    rows = y.numel() // hidden
+    tsum = torch.empty_like(y) if want_sum else None
+    o32 = torch.empty_like(y) if want_f32 else None
+    o16 = torch.empty(y.shape, dtype=torch.float16, device=y.device) if want_f16 else None
+    check(LIB.pe_residual_layernorm(y.data_ptr(), resid.data_ptr(), gamma.data_ptr(), beta.data_ptr(), float(eps),
+                                    _ptr(tsum), _ptr(o32), _ptr(o16), rows, hidden, _stream()))
+    return tsum, o32, o16
+
+
 _EPI_OUT = {_lib.PE_EPI_F16: torch.float16, _lib.PE_EPI_GELU_F16: torch.float16, _lib.PE_EPI_RESID_F32: torch.float32,
             _lib.PE_EPI_F32: torch.float32, _lib.PE_EPI_TANH_F32: torch.float32}
 

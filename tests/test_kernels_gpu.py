@@ -37,6 +37,18 @@ def test_layernorm(ops, rows, hidden):
     torch.testing.assert_close(o16.cpu().float(), want, rtol=1e-3, atol=1e-3)   # one fp16 rounding
 
 
+def test_residual_layernorm(ops):
+    """t = y + resid (returned as the new residual stream) and LayerNorm(t) in one pass."""
+    gen = torch.Generator().manual_seed(5)
+    y, r = torch.randn(394, 768, generator=gen), torch.randn(394, 768, generator=gen) * 2
+    g, b = 1 + 0.1 * torch.randn(768, generator=gen), 0.1 * torch.randn(768, generator=gen)
+    tsum, o32, o16 = ops.residual_layernorm(y.cuda(), r.cuda(), g.cuda(), b.cuda(), 1e-12, want_f32=True)
+    assert torch.equal(tsum.cpu(), y + r)
+    want = F.layer_norm(y + r, (768,), g, b, 1e-12)
+    torch.testing.assert_close(o32.cpu(), want, rtol=2e-5, atol=2e-5)
+    torch.testing.assert_close(o16.cpu().float(), want, rtol=1e-3, atol=1e-3)
+
+
 def _gemm_case(m, n, k, seed):
     gen = torch.Generator().manual_seed(seed)
     a = torch.randn(m, k, generator=gen).half()
@@ -130,3 +142,17 @@ def test_attention(ops, batch, tokens, heads):
     got = ops.attention(qkv.cuda(), batch, tokens, heads)
     # P is rounded to fp16 before P.V and the output is fp16: 2e-3 absolute on O(1) values
     torch.testing.assert_close(got.cpu().float(), want, rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize('plan', ['1,1,224', '1,1,96', '2,2,128', '1,1,64'])
+def test_linear_forced_tile_plans(ops, plan, monkeypatch):
+    """Tile plans the heuristic may not pick (BN not a multiple of the TMA-store box, clusters) stay correct."""
+    lib = _lib()
+    monkeypatch.setenv('PE_GEMM_FORCE', plan)
+    for epi_name in ('PE_EPI_F16', 'PE_EPI_F32'):
+        epi = getattr(lib, epi_name)
+        a, w, bias, resid = _gemm_case(1576, 2304, 768, 9)
+        want = _gemm_ref(a, w, bias, resid, epi)
+        got = ops.linear(a.cuda(), w.cuda(), bias.cuda(), epi)
+        tol = 2e-3 if 'F16' in epi_name else 5e-5
+        torch.testing.assert_close(got.cpu().float(), want, rtol=tol, atol=tol)
