@@ -123,15 +123,44 @@ def load_peaks() -> dict:
 # ---------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port, timed (cpu_baseline and --impl reference)
 # ---------------------------------------------------------------------------------------------------
+def usable_cores() -> int:
+    """Host threads this process may really use: affinity mask, capped by a cgroup CPU quota if one is set."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    try:
+        with open('/sys/fs/cgroup/cpu.max', encoding='utf-8') as fh:
+            quota, period = fh.read().split()
+        if quota != 'max':
+            cores = max(1, min(cores, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return cores
+
+
 def cpu_forward_timer(spec, ubatch: int, seq: int):
-    """Returns (callable running one micro-batch through the whole model on the CPU, cores used)."""
+    """Returns (callable running one micro-batch through the whole model on the CPU, threads used).
+
+    "All the host threads it can use": the thread count is calibrated on one encoder block over
+    {8, 16, 32, 64, all usable} - on a many-core shared box torch's fp32 GEMMs get SLOWER past a point."""
     from oracle import shards as osh   # the one place bench.py may execute oracle/ (as the timed CPU baseline)
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     weights = synth_weights(spec, seed=0)
     model = osh.PreparedShard(spec, weights, 1, spec.layers)
     x = synth_input(spec, ubatch, seed=1, seq_len=seq or 128)
-    return (lambda: model.forward(x)), cores
+    limit = usable_cores()
+    block = osh.PreparedShard(spec, weights, 1, 4)
+    best, best_t = 1, float('inf')
+    for n in sorted({min(c, limit) for c in (8, 16, 32, 64, limit)}):
+        torch.set_num_threads(n)
+        block.forward(x)
+        t0 = time.perf_counter()
+        block.forward(x)
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = n, dt
+    torch.set_num_threads(best)
+    return (lambda: model.forward(x)), best
 
 
 def cpu_baseline(spec, ubatch: int, seq: int, unit: str, budget_s: float = 15.0) -> dict:
@@ -145,7 +174,7 @@ def cpu_baseline(spec, ubatch: int, seq: int, unit: str, budget_s: float = 15.0)
     dt = time.perf_counter() - t0
     return {'value': n * ubatch / dt, 'unit': unit, 'cores': cores, 'kind': 'port',
             'sample': f"{n} micro-batches of {ubatch} through all {spec.layers} sub-layers, torch fp32 CPU "
-                      f"({dt:.1f} s), 1 process x {cores} threads"}
+                      f"({dt:.1f} s), 1 process x {cores} threads (best of a thread-count calibration)"}
 
 
 def run_reference_arm(args, spec, ubatch, seq, metric, unit, workload):

@@ -32,10 +32,13 @@ TAG_CMD = 10          # [cmd, n_tensors, sender rank]
 _CMD_EXIT = -1        # internal: unblocks the receiver's CommandThread at shutdown
 TAG_CMD_META = 11     # per command tensor: [n_bytes] then pickled (dtype, shape)
 TAG_CMD_DATA = 12
-TAG_DATA_HDR = 0      # [header_bytes]; 0 = same header as the previous payload on this hop; -1 = hop closing
-TAG_DATA_META = 1     # pickled payload description
-TAG_DATA_CPU = 2      # CPU tensors of the payload, in order
+TAG_DATA_ENV = 0      # one fixed-size envelope per payload (see _ENVELOPE)
+TAG_DATA_EXT = 1      # overflow of an envelope that did not fit
 
+# Envelope: uint8[_ENVELOPE] = int64 meta_len | int64 cpu_len | pickled payload description | CPU tensor bytes.
+# meta_len == 0: same description as the previous payload of this hop (shapes are static per schedule, so steady
+# state costs ONE small Gloo message per payload next to the NCCL transfer); meta_len == -1: the hop is closing.
+_ENVELOPE = 2048
 _POLL_SEC = 0.0002
 _RECV_SLOTS = 4       # ring of device receive buffers per payload position
 
@@ -157,7 +160,7 @@ class _RequestWaiter(threading.Thread):
 _STOP_GRACE_SEC = 10.0
 
 
-def _poll(req, stop_evt: threading.Event) -> bool:
+def _poll(req, stop_evt: threading.Event) -> bool:  # noqa: C901
     """Wait for a distributed request. Once `stop_evt` is set the peer is expected to unblock us with its
     closing message; only after a grace period is the request abandoned (False). Abandoning leaves a daemon
     thread inside `wait()`, which PyTorch turns into an abort at process exit - the reference's teardown race
@@ -207,17 +210,15 @@ class AbstractTensorExchangeThread(threading.Thread):
             self._stream = torch.cuda.Stream(device=self._device)
 
 
-def _describe(objs: tuple, is_tuple: bool):
-    """Picklable description of a payload + the CPU tensors and CUDA tensors to ship."""
-    items, cpu, cuda = [], [], []
+def _signature(objs: tuple, is_tuple: bool):
+    """Cheap hashable description of a payload's structure; only pickled when it changes."""
+    sig = [is_tuple]
     for obj in objs:
         if isinstance(obj, torch.Tensor):
-            plane = 'cuda' if obj.is_cuda else 'cpu'
-            items.append((plane, obj.dtype, tuple(obj.shape)))
-            (cuda if obj.is_cuda else cpu).append(obj)
+            sig.append(('cuda' if obj.is_cuda else 'cpu', obj.dtype, tuple(obj.shape)))
         else:
-            items.append(('obj', pickle.dumps(obj), None))   # non-tensor objects ride in the header (util.py:28-38)
-    return {'tuple': is_tuple, 'items': items}, cpu, cuda
+            sig.append(('obj', pickle.dumps(obj), None))   # non-tensor objects ride in the description (util.py:28-38)
+    return tuple(sig)
 
 
 class TensorSendThread(AbstractTensorExchangeThread):
@@ -227,7 +228,7 @@ class TensorSendThread(AbstractTensorExchangeThread):
         super().__init__()
         self._queue_out = queue_out
         self._dst_rank = dst_rank
-        self._last_meta = None
+        self._last_sig = None
         self._inflight = collections.deque()
 
     def stop(self) -> None:
@@ -243,10 +244,27 @@ class TensorSendThread(AbstractTensorExchangeThread):
         try:
             self._run(group)
         finally:
-            try:   # tell the receiver this hop is closing, so that its pending header receive completes
-                dist.send(torch.tensor([-1], dtype=torch.int64), dst=self._dst_rank, tag=TAG_DATA_HDR)
+            try:   # tell the receiver this hop is closing, so that its pending envelope receive completes
+                env = torch.zeros(_ENVELOPE, dtype=torch.uint8)
+                env[:8] = torch.tensor([-1], dtype=torch.int64).view(torch.uint8)
+                dist.send(env, dst=self._dst_rank, tag=TAG_DATA_ENV)
             except Exception:   # pylint: disable=broad-except
                 pass
+
+    def _send_envelope(self, sig, cpu: List[torch.Tensor]) -> None:
+        meta = b'' if sig == self._last_sig else pickle.dumps(sig)
+        self._last_sig = sig
+        blob = b''.join(t.contiguous().view(-1).view(torch.uint8).numpy().tobytes() for t in cpu if t.numel() > 0)
+        env = torch.zeros(_ENVELOPE, dtype=torch.uint8)
+        env[:16] = torch.tensor([len(meta), len(blob)], dtype=torch.int64).view(torch.uint8)
+        body = meta + blob
+        if len(body) <= _ENVELOPE - 16:
+            if body:
+                env[16:16 + len(body)] = torch.frombuffer(bytearray(body), dtype=torch.uint8)
+            dist.send(env, dst=self._dst_rank, tag=TAG_DATA_ENV)
+        else:
+            dist.send(env, dst=self._dst_rank, tag=TAG_DATA_ENV)
+            dist.send(torch.frombuffer(bytearray(body), dtype=torch.uint8), dst=self._dst_rank, tag=TAG_DATA_EXT)
 
     def _run(self, group):
         while not self._evt_stop_thread.is_set():
@@ -260,32 +278,25 @@ class TensorSendThread(AbstractTensorExchangeThread):
             data = payload.data
             is_tuple = isinstance(data, tuple)
             objs = data if is_tuple else (data,)
-            desc, cpu, cuda = _describe(objs, is_tuple)
-            meta = pickle.dumps(desc)
-            # header: only re-sent when the payload's structure changes (shapes are static per schedule)
-            if meta == self._last_meta:
-                dist.send(torch.zeros(1, dtype=torch.int64), dst=self._dst_rank, tag=TAG_DATA_HDR)
-            else:
-                buf = torch.frombuffer(bytearray(meta), dtype=torch.uint8)
-                dist.send(torch.tensor([buf.numel()], dtype=torch.int64), dst=self._dst_rank, tag=TAG_DATA_HDR)
-                dist.send(buf, dst=self._dst_rank, tag=TAG_DATA_META)
-                self._last_meta = meta
+            tensors = [o for o in objs if isinstance(o, torch.Tensor)]
+            cpu = [t for t in tensors if not t.is_cuda]
+            cuda = [t for t in tensors if t.is_cuda]
+            self._send_envelope(_signature(objs, is_tuple), cpu)
             self._call_pre_hooks()
-            for tensor in cpu:
-                if tensor.numel() > 0:
-                    dist.send(tensor.contiguous().view(-1), dst=self._dst_rank, tag=TAG_DATA_CPU)
             if cuda:
                 if group is None:
                     raise RuntimeError("CUDA tensors in a payload need the NCCL data plane (DistP2pContext with CUDA)")
                 with torch.cuda.stream(self._stream):
                     if payload.ready is not None:
                         self._stream.wait_event(payload.ready)
-                    ops = []
                     for tensor in cuda:
                         tensor.record_stream(self._stream)
-                        ops.append(dist.P2POp(dist.isend, tensor.contiguous(), self._dst_rank, group=group))
-                    for work in dist.batch_isend_irecv(ops):   # one ncclGroup -> one kernel for the whole payload
-                        work.wait()                            # stream-level wait only: the host does not block
+                    if len(cuda) == 1:
+                        dist.isend(cuda[0], self._dst_rank, group=group).wait()   # stream-level wait: host does not block
+                    else:
+                        ops = [dist.P2POp(dist.isend, t, self._dst_rank, group=group) for t in cuda]
+                        for work in dist.batch_isend_irecv(ops):   # one ncclGroup for the whole payload
+                            work.wait()
                     done = torch.cuda.Event()
                     done.record(self._stream)
                 if payload.on_consumed is not None:
@@ -296,7 +307,7 @@ class TensorSendThread(AbstractTensorExchangeThread):
                     self._inflight.popleft().synchronize()
             elif payload.on_consumed is not None:
                 payload.on_consumed(None)
-            self._call_post_hooks(tuple(t for t in objs if isinstance(t, torch.Tensor)))
+            self._call_post_hooks(tuple(tensors))
 
 
 class TensorRecvThread(AbstractTensorExchangeThread):
@@ -306,7 +317,7 @@ class TensorRecvThread(AbstractTensorExchangeThread):
         super().__init__()
         self._queue_in = queue_in
         self._src_rank = src_rank
-        self._desc = None
+        self._sig = None
         self._rings = {}
         self._count = 0
 
@@ -328,27 +339,40 @@ class TensorRecvThread(AbstractTensorExchangeThread):
         """Receive payloads and enqueue them."""
         self._enter_device()
         group = DistP2pContext.hop_group(self._src_rank, dist.get_rank())
+        env = torch.zeros(_ENVELOPE, dtype=torch.uint8)
         while True:
-            hdr = torch.zeros(1, dtype=torch.int64)
-            if not _poll(dist.irecv(hdr, src=self._src_rank, tag=TAG_DATA_HDR), self._evt_stop_thread):
-                return
-            if int(hdr[0]) < 0:
+            # blocks until the sender's next payload or its closing envelope (sent by its shutdown); no polling
+            # thread per message as in the reference (`p2p/__init__.py:224-232`) - the closing handshake makes a
+            # plain blocking receive safe to shut down
+            try:
+                dist.recv(env, src=self._src_rank, tag=TAG_DATA_ENV)
+            except Exception:   # pylint: disable=broad-except
+                return          # the process group went away under us
+            meta_len, cpu_len = env[:16].view(torch.int64).tolist()
+            if meta_len < 0:
                 return   # the sender closed the hop
-            if int(hdr[0]) > 0:
-                buf = torch.empty(int(hdr[0]), dtype=torch.uint8)
-                dist.recv(buf, src=self._src_rank, tag=TAG_DATA_META)
-                self._desc = pickle.loads(buf.numpy().tobytes())
-            desc = self._desc
+            if meta_len + cpu_len <= _ENVELOPE - 16:
+                body = env[16:16 + meta_len + cpu_len].numpy().tobytes()
+            else:
+                ext = torch.empty(meta_len + cpu_len, dtype=torch.uint8)
+                dist.recv(ext, src=self._src_rank, tag=TAG_DATA_EXT)
+                body = ext.numpy().tobytes()
+            if meta_len > 0:
+                self._sig = pickle.loads(body[:meta_len])
+            sig = self._sig
             self._call_pre_hooks()
             objs: List[Any] = []
             cuda_slots = []
-            for pos, (plane, dtype, shape) in enumerate(desc['items']):
+            off = meta_len
+            for pos, (plane, dtype, shape) in enumerate(sig[1:]):
                 if plane == 'obj':
                     objs.append(pickle.loads(dtype))
                 elif plane == 'cpu':
                     tensor = torch.empty(shape, dtype=dtype)
-                    if tensor.numel() > 0:
-                        dist.recv(tensor.view(-1), src=self._src_rank, tag=TAG_DATA_CPU)
+                    nbytes = tensor.numel() * tensor.element_size()
+                    if nbytes > 0:
+                        tensor.view(-1).view(torch.uint8).copy_(torch.frombuffer(bytearray(body[off:off + nbytes]), dtype=torch.uint8))
+                        off += nbytes
                     objs.append(tensor)
                 else:
                     slot = self._slot(pos, dtype, shape)
@@ -358,13 +382,15 @@ class TensorRecvThread(AbstractTensorExchangeThread):
             on_consumed = None
             if cuda_slots:
                 with torch.cuda.stream(self._stream):
-                    ops = []
                     for slot in cuda_slots:
                         if slot[1] is not None:
                             self._stream.wait_event(slot[1])    # the previous consumer of this buffer is done
-                        ops.append(dist.P2POp(dist.irecv, slot[0], self._src_rank, group=group))
-                    for work in dist.batch_isend_irecv(ops):
-                        work.wait()
+                    if len(cuda_slots) == 1:
+                        dist.irecv(cuda_slots[0][0], self._src_rank, group=group).wait()
+                    else:
+                        ops = [dist.P2POp(dist.irecv, slot[0], self._src_rank, group=group) for slot in cuda_slots]
+                        for work in dist.batch_isend_irecv(ops):
+                            work.wait()
                     ready = torch.cuda.Event()
                     ready.record(self._stream)
 
@@ -373,7 +399,7 @@ class TensorRecvThread(AbstractTensorExchangeThread):
                         slot[1] = evt
             self._count += 1
             self._call_post_hooks(tuple(t for t in objs if isinstance(t, torch.Tensor)))
-            data = tuple(objs) if desc['tuple'] else objs[0]
+            data = tuple(objs) if sig[0] else objs[0]
             with self._queue_in.condition:
                 while self._queue_in.full():
                     if self._evt_stop_thread.is_set():

@@ -118,6 +118,7 @@ class GpuTransformerShard(ModuleShard):
 
     def _run_blocks(self, data: TransformerShardData) -> TransformerShardData:
         in0 = data[0] if isinstance(data, tuple) else data
+        self.stage.ensure_shape(in0)   # BERT: the sequence length is the input's; output rings are sized after this
         out = self._stage_out(in0.shape[0])
         res = self.stage.forward(data, out=out, use_graph=self.use_cuda_graph)
         self._mark_inputs_consumed()

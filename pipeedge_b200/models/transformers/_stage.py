@@ -141,6 +141,11 @@ class EncoderStage:
         self._handle = ctypes.c_void_p()
         self._create()
 
+    def ensure_shape(self, in0: torch.Tensor) -> None:
+        """Adopt the payload's sequence length / micro-batch (callers must do this BEFORE sizing output buffers)."""
+        if in0.shape[1] != self.tokens or in0.shape[0] > self.max_ubatch:
+            self.resize(in0.shape[1], max(in0.shape[0], self.max_ubatch))
+
     def close(self) -> None:
         """Release the library-owned workspace."""
         if getattr(self, '_handle', None) is not None and self._handle.value:
@@ -180,8 +185,7 @@ class EncoderStage:
         else:
             in0, in1 = data, None
         ubatch = in0.shape[0]
-        if in0.shape[1] != self.tokens or ubatch > self.max_ubatch:
-            self.resize(in0.shape[1], max(ubatch, self.max_ubatch))
+        self.ensure_shape(in0)
         for t in (in0, in1):
             if t is not None and (not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous()):
                 raise ValueError("EncoderStage.forward: payloads must be contiguous fp32 CUDA tensors")

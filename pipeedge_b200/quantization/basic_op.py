@@ -16,6 +16,20 @@ def compression_factor(quant_bit: torch.Tensor) -> torch.Tensor:
     return torch.div(32, quant_bit)
 
 
+_PASSTHROUGH_META = {}
+
+
+def _passthrough_meta(items: int, item_shape: tuple):
+    """The four host-side tensors of an un-quantised payload; constant per shape, so built once (read-only)."""
+    key = (items, item_shape)
+    meta = _PASSTHROUGH_META.get(key)
+    if meta is None:
+        meta = (torch.tensor(item_shape).expand(items, -1).clone(), torch.ones(items), torch.zeros(items),
+                torch.zeros(items, dtype=torch.int8))
+        _PASSTHROUGH_META[key] = meta
+    return meta
+
+
 def tensor_encode_outerdim(batched_tensor: torch.Tensor, quant_bit: int, clamp: bool = False) -> List[torch.Tensor]:
     """Per-item quantisation of a micro-batched fp32 CUDA tensor (`basic_op.py:166-170`).
 
@@ -24,8 +38,7 @@ def tensor_encode_outerdim(batched_tensor: torch.Tensor, quant_bit: int, clamp: 
     items = batched_tensor.shape[0]
     item_shape = tuple(batched_tensor.shape[1:])
     if quant_bit == 0:   # passthrough layout of `tensor_encode` (`basic_op.py:120-122`)
-        return [batched_tensor, torch.tensor(item_shape).expand(items, -1).clone(), torch.ones(items),
-                torch.zeros(items), torch.zeros(items, dtype=torch.int8)]
+        return [batched_tensor, *_passthrough_meta(items, item_shape)]
     comm, scale, shift, _alpha = ops.quant_encode(batched_tensor, int(quant_bit), clamp)
     shape = torch.tensor(item_shape, dtype=torch.int32).expand(items, -1).clone()
     return [comm, shape, scale, shift, torch.full((items,), int(quant_bit), dtype=torch.int8)]
