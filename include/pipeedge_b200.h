@@ -196,6 +196,21 @@ int pe_bert_embed(const void* ids, const void* pos_ids, const void* word, const 
                   const void* gamma, const void* beta, float eps, void* out, int batch, int seq, int hidden,
                   void* stream);
 
+/* ---- Inter-stage hop (native fast path) --------------------------------------------------------
+ * Replaces `TensorSendThread.run` / `TensorRecvThread.run` + `_send_tensor` / `_recv_tensor`
+ * (`p2p/__init__.py:96-258`) for the device tensors of a payload: one call per payload and side, over a
+ * dedicated 2-rank NCCL communicator per directed hop; `fd` is the hop's connected Unix-domain socket (owned by
+ * the caller) carrying the 16-byte envelope headers. Events are `cudaEvent_t`, streams `cudaStream_t`. */
+typedef struct pe_hop pe_hop;
+int pe_hop_available(void);
+int pe_hop_open(int fd, int is_sender, pe_hop** out);
+int pe_hop_close(pe_hop* hop);
+int pe_hop_send(pe_hop* hop, const void* const* ptrs, const size_t* bytes, int n, void* ready_event, void* stream,
+                void* done_event, int write_envelope);
+int pe_hop_wait_envelope(pe_hop* hop, long long* head2);
+int pe_hop_recv(pe_hop* hop, void* const* ptrs, const size_t* bytes, void* const* free_events, int n, void* stream,
+                void* ready_event);
+
 /* ---- Debug / bring-up ------------------------------------------------------------------------
  * Reference GEMM on CUDA cores (fp16 inputs, fp32 accumulate, same epilogues). Used ONLY by tests to
  * localise a failure to the tcgen05 kernel; never selected by the product path. */

@@ -5,7 +5,7 @@ machine without an sm_100 GPU fails with `PipeEdgeB200Error` (PE_ERR_DEVICE).
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_size_t, c_uint64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_longlong, c_size_t, c_uint64, c_void_p
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, 'libpipeedge_b200.so')
@@ -57,6 +57,12 @@ SYMBOLS = {
     'pe_stage_kernel_count': (c_int, [c_void_p]),
     'pe_patch_embed': (c_int, [c_void_p] * 7 + [c_int] * 6 + [c_void_p]),
     'pe_bert_embed': (c_int, [c_void_p] * 7 + [c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'pe_hop_available': (c_int, []),
+    'pe_hop_open': (c_int, [c_int, c_int, POINTER(c_void_p)]),
+    'pe_hop_close': (c_int, [c_void_p]),
+    'pe_hop_send': (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_size_t), c_int, c_void_p, c_void_p, c_void_p, c_int]),
+    'pe_hop_wait_envelope': (c_int, [c_void_p, POINTER(c_longlong)]),
+    'pe_hop_recv': (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_size_t), POINTER(c_void_p), c_int, c_void_p, c_void_p]),
     'pe_debug_gemm_trace': (c_int, [c_void_p]),
     'pe_debug_linear_simt': (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
 }

@@ -4,6 +4,9 @@ Same classes and call contract (`DistP2pContext`, `DistP2pPipelineStage` with `e
 `register_*_hook`s, `work_cb` / `results_cb`, FIFO per hop, back-pressure through size-1 queues), rebuilt
 for one rank per B200:
 
+* Per-payload control data (the payload description, only when it changes, and any CPU tensors) goes over one
+  Unix-domain socket per hop: a Gloo message costs ~170 us of host time (measured), a local socket ~10 us, and at
+  8 stages a micro-batch of 8 images is only ~150 us of GPU work per stage. Single node only, as is the target.
 * The DEVICE of a tensor picks its plane. CUDA tensors (activations, int8 codes, per-item scales) travel
   over a dedicated 2-rank NCCL communicator per hop direction on a side stream, ordered against the compute
   stream with CUDA events, so the hop of micro-batch i overlaps the compute of micro-batch i+1 without the
@@ -18,11 +21,15 @@ for one rank per B200:
 Without CUDA (the CPU test-suite) everything rides Gloo and the classes behave like the reference's.
 """
 import collections
+import os
 import pickle
 import queue
+import socket
+import struct
 import threading
 import time
 from typing import Any, Callable, List, Optional, Tuple
+import ctypes
 import torch
 import torch.distributed as dist
 from .. import DistCmdHandler, DistContext
@@ -32,15 +39,82 @@ TAG_CMD = 10          # [cmd, n_tensors, sender rank]
 _CMD_EXIT = -1        # internal: unblocks the receiver's CommandThread at shutdown
 TAG_CMD_META = 11     # per command tensor: [n_bytes] then pickled (dtype, shape)
 TAG_CMD_DATA = 12
-TAG_DATA_ENV = 0      # one fixed-size envelope per payload (see _ENVELOPE)
-TAG_DATA_EXT = 1      # overflow of an envelope that did not fit
 
-# Envelope: uint8[_ENVELOPE] = int64 meta_len | int64 cpu_len | pickled payload description | CPU tensor bytes.
-# meta_len == 0: same description as the previous payload of this hop (shapes are static per schedule, so steady
-# state costs ONE small Gloo message per payload next to the NCCL transfer); meta_len == -1: the hop is closing.
-_ENVELOPE = 2048
+# Envelope on the hop's socket: int64 meta_len | int64 cpu_len | pickled payload description | CPU tensor bytes.
+# meta_len == 0: same description as the previous payload of this hop (shapes are static per schedule);
+# meta_len == -1: the hop is closing. cpu_len == -1: the payload's CPU tensors are the very same objects as the
+# previous payload's (the constant shape / scale / bit-width tensors of the QuantPipe wire format), so the receiver
+# reuses its copies. Every Python-level operation here costs a GIL hand-off between the stage's threads, which
+# measured at tens of microseconds each - the steady-state path is therefore two comparisons and a 16-byte write.
+_ENV_HEAD = struct.Struct('<qq')
 _POLL_SEC = 0.0002
-_RECV_SLOTS = 4       # ring of device receive buffers per payload position
+
+
+def queue_depth() -> int:
+    """Capacity of the stage's in / out / res queues. The reference uses 1 (`p2p/__init__.py:374-376`); a thread
+    hand-off costs a wake-up of ~0.1 ms on a busy host, so with capacity 1 producer and consumer run in lock-step.
+    `PIPEEDGE_QUEUE_DEPTH` > 1 lets hand-offs overlap at the price of that many more micro-batches in flight."""
+    return max(1, int(os.environ.get('PIPEEDGE_QUEUE_DEPTH', '1')))
+
+
+def ring_slots() -> int:
+    """Device buffers per ring: queued + in transfer + being produced + being consumed."""
+    return queue_depth() + 3
+
+
+def _native_lib():
+    """`libpipeedge_b200.so` when this process drives a GPU (native hop fast path), else None."""
+    if not torch.cuda.is_available():
+        return None
+    from ..._lib import LIB   # pylint: disable=import-outside-toplevel
+    return LIB if LIB.pe_hop_available() else None
+
+
+class _NativeHop:
+    """`pe_hop_*`: one C call per payload and side moves the device tensors over the hop's NCCL communicator."""
+
+    def __init__(self, lib, sock: socket.socket, is_sender: bool):
+        from ..._lib import check   # pylint: disable=import-outside-toplevel
+        self._lib, self._check = lib, check
+        self._handle = ctypes.c_void_p()
+        check(lib.pe_hop_open(sock.fileno(), 1 if is_sender else 0, ctypes.byref(self._handle)))
+
+    def close(self) -> None:
+        if self._handle:
+            self._lib.pe_hop_close(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    @staticmethod
+    def _arrays(tensors):
+        n = len(tensors)
+        ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in tensors])
+        sizes = (ctypes.c_size_t * n)(*[t.numel() * t.element_size() for t in tensors])
+        return ptrs, sizes, n
+
+    def send(self, tensors, ready, stream, done, write_envelope: bool) -> None:
+        ptrs, sizes, n = self._arrays(tensors)
+        self._check(self._lib.pe_hop_send(self._handle, ptrs, sizes, n, None if ready is None else ready.cuda_event,
+                                          stream.cuda_stream, done.cuda_event, 1 if write_envelope else 0))
+
+    def wait_envelope(self):
+        head = (ctypes.c_longlong * 2)()
+        rc = self._lib.pe_hop_wait_envelope(self._handle, head)   # blocks with the GIL released
+        if rc == 1:
+            return None
+        self._check(rc)
+        return int(head[0]), int(head[1])
+
+    def recv(self, slots, stream, ready) -> None:
+        ptrs, sizes, n = self._arrays([slot[0] for slot in slots])
+        guards = (ctypes.c_void_p * n)(*[None if slot[1] is None else slot[1].cuda_event for slot in slots])
+        self._check(self._lib.pe_hop_recv(self._handle, ptrs, sizes, guards, n, stream.cuda_stream, ready.cuda_event))
+
+
+def _fresh_event(stream) -> 'torch.cuda.Event':
+    """An event whose CUDA handle exists (torch creates it lazily on the first record)."""
+    evt = torch.cuda.Event()
+    evt.record(stream)
+    return evt
 
 
 class ConditionQueue(queue.Queue):
@@ -80,17 +154,29 @@ class DistP2pContext(DistContext):
         super().__init__(ipg_args, ipg_kwargs)
         self._thread_cmd = CommandThread(cmd_cb)
         self._hop_groups = {}
+        self._listener = None
+        self._sock_path = None
+        self._inbound = {}                      # src rank -> accepted connection
+        self._inbound_cond = threading.Condition()
 
     def init(self) -> None:
         """Initialize the distributed context and threads."""
         super().init()
         dist.init_process_group(*self._init_args, **self._init_kwargs)
-        if torch.cuda.is_available() and self._world_size > 1:
-            # every rank must create every group, in the same order
+        if torch.cuda.is_available() and self._world_size > 1 and _native_lib() is None:
+            # fallback data plane (torch.distributed NCCL): every rank must create every group, in the same order
             for src in range(self._world_size):
                 for dst in range(self._world_size):
                     if src != dst:
                         self._hop_groups[(src, dst)] = dist.new_group(ranks=[src, dst], backend='nccl')
+        if self._world_size > 1:
+            self._sock_path = self.sock_path(self._rank)
+            if os.path.exists(self._sock_path):
+                os.unlink(self._sock_path)
+            self._listener = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            self._listener.bind(self._sock_path)
+            self._listener.listen(self._world_size)
+            threading.Thread(target=self._accept_loop, daemon=True).start()
         DistP2pContext._instance = self
         if self._world_size > 1:   # nobody can send a command to a world of one
             self._thread_cmd.start()
@@ -106,7 +192,58 @@ class DistP2pContext(DistContext):
             self._thread_cmd.join(timeout=_STOP_GRACE_SEC + 5)
             dist.barrier()
         DistP2pContext._instance = None
+        if self._listener is not None:
+            try:
+                self._listener.close()
+                os.unlink(self._sock_path)
+            except OSError:
+                pass
+            self._listener = None
         dist.destroy_process_group()
+
+    @staticmethod
+    def sock_path(rank: int) -> str:
+        """Path of `rank`'s hop listener (ranks share a node; MASTER_PORT keeps concurrent jobs apart)."""
+        return f"/tmp/pipeedge_b200_{os.environ.get('MASTER_PORT', '0')}_{rank}.sock"
+
+    def _accept_loop(self) -> None:
+        while True:
+            try:
+                conn, _ = self._listener.accept()
+            except OSError:
+                return   # listener closed at shutdown
+            src = struct.unpack('<i', _recv_exact(conn, 4))[0]
+            with self._inbound_cond:
+                self._inbound[src] = conn
+                self._inbound_cond.notify_all()
+
+    @classmethod
+    def accept_from(cls, src: int, timeout: float = 120.0) -> socket.socket:
+        """The inbound hop connection from rank `src` (waits for it to connect)."""
+        inst = cls._instance
+        assert inst is not None, "DistP2pContext is not initialised"
+        with inst._inbound_cond:   # pylint: disable=protected-access
+            if not inst._inbound_cond.wait_for(lambda: src in inst._inbound, timeout):
+                raise TimeoutError(f"rank {src} never opened its hop to this rank")
+            return inst._inbound.pop(src)
+
+    @classmethod
+    def connect_to(cls, dst: int, timeout: float = 120.0) -> socket.socket:
+        """Open the outbound hop connection to rank `dst` (retries until its listener is up)."""
+        inst = cls._instance
+        assert inst is not None, "DistP2pContext is not initialised"
+        deadline = time.monotonic() + timeout
+        while True:
+            sock = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            try:
+                sock.connect(cls.sock_path(dst))
+                sock.sendall(struct.pack('<i', inst._rank))   # pylint: disable=protected-access
+                return sock
+            except OSError:
+                sock.close()
+                if time.monotonic() > deadline:
+                    raise
+                time.sleep(0.01)
 
     @classmethod
     def hop_group(cls, src: int, dst: int):
@@ -136,6 +273,18 @@ class DistP2pContext(DistContext):
                     reqs.append(dist.isend(tensor.view(-1), dst=dst, tag=TAG_CMD_DATA))
         for req in reqs:
             req.wait()
+
+
+def _recv_exact(conn: socket.socket, n: int) -> bytes:
+    """Read exactly n bytes (b'' on EOF)."""
+    chunks = []
+    while n > 0:
+        chunk = conn.recv(min(n, 1 << 20))
+        if not chunk:
+            return b''
+        chunks.append(chunk)
+        n -= len(chunk)
+    return b''.join(chunks)
 
 
 class _RequestWaiter(threading.Thread):
@@ -184,6 +333,7 @@ class AbstractTensorExchangeThread(threading.Thread):
         super().__init__(daemon=True)
         self._pre_hooks = []
         self._post_hooks = []
+        self.stats = {'wait_s': 0.0, 'busy_s': 0.0, 'n': 0}   # time blocked on the queue / peer vs. doing work
         self._evt_stop_thread = threading.Event()
         self._device = torch.cuda.current_device() if torch.cuda.is_available() else None
         self._stream = None
@@ -229,6 +379,9 @@ class TensorSendThread(AbstractTensorExchangeThread):
         self._queue_out = queue_out
         self._dst_rank = dst_rank
         self._last_sig = None
+        self._last_cpu: List[torch.Tensor] = []
+        self._sock = None
+        self._hop = None
         self._inflight = collections.deque()
 
     def stop(self) -> None:
@@ -241,33 +394,47 @@ class TensorSendThread(AbstractTensorExchangeThread):
         """Dequeue payloads and send them."""
         self._enter_device()
         group = DistP2pContext.hop_group(dist.get_rank(), self._dst_rank)
+        if self._sock is None:
+            self.open_hop()
         try:
             self._run(group)
         finally:
-            try:   # tell the receiver this hop is closing, so that its pending envelope receive completes
-                env = torch.zeros(_ENVELOPE, dtype=torch.uint8)
-                env[:8] = torch.tensor([-1], dtype=torch.int64).view(torch.uint8)
-                dist.send(env, dst=self._dst_rank, tag=TAG_DATA_ENV)
-            except Exception:   # pylint: disable=broad-except
+            if self._hop is not None:
+                if self._inflight:
+                    self._inflight[-1].synchronize()
+                self._hop.close()
+            try:   # tell the receiver this hop is closing, so that its blocking receive returns
+                self._sock.sendall(_ENV_HEAD.pack(-1, 0))
+                self._sock.close()
+            except OSError:
                 pass
 
-    def _send_envelope(self, sig, cpu: List[torch.Tensor]) -> None:
-        meta = b'' if sig == self._last_sig else pickle.dumps(sig)
+    def open_hop(self) -> None:
+        """Connect to the receiver and, on a GPU, join the hop's NCCL communicator (blocks until the peer does)."""
+        self._sock = DistP2pContext.connect_to(self._dst_rank)
+        lib = _native_lib()
+        self._hop = _NativeHop(lib, self._sock, True) if lib is not None else None
+
+    def _send_envelope(self, sig, cpu: List[torch.Tensor], defer_fast: bool = False) -> bool:
+        """Write the payload's envelope; returns True if it was (or, with `defer_fast`, is to be) the 16-byte
+        steady-state header."""
+        same_sig = sig == self._last_sig
+        last_cpu = self._last_cpu
+        if same_sig and len(cpu) == len(last_cpu) and all(a is b for a, b in zip(cpu, last_cpu)):
+            if not defer_fast:
+                self._sock.sendall(_ENV_HEAD.pack(0, -1))   # steady state: nothing but the header
+            return True
+        meta = b'' if same_sig else pickle.dumps(sig)
         self._last_sig = sig
-        blob = b''.join(t.contiguous().view(-1).view(torch.uint8).numpy().tobytes() for t in cpu if t.numel() > 0)
-        env = torch.zeros(_ENVELOPE, dtype=torch.uint8)
-        env[:16] = torch.tensor([len(meta), len(blob)], dtype=torch.int64).view(torch.uint8)
-        body = meta + blob
-        if len(body) <= _ENVELOPE - 16:
-            if body:
-                env[16:16 + len(body)] = torch.frombuffer(bytearray(body), dtype=torch.uint8)
-            dist.send(env, dst=self._dst_rank, tag=TAG_DATA_ENV)
-        else:
-            dist.send(env, dst=self._dst_rank, tag=TAG_DATA_ENV)
-            dist.send(torch.frombuffer(bytearray(body), dtype=torch.uint8), dst=self._dst_rank, tag=TAG_DATA_EXT)
+        self._last_cpu = list(cpu)   # keeps the objects alive, so `is` cannot match a recycled id
+        parts = [t.contiguous().view(-1).view(torch.uint8).numpy().tobytes() for t in cpu if t.numel() > 0]
+        blob_len = sum(len(part) for part in parts)
+        self._sock.sendall(b''.join([_ENV_HEAD.pack(len(meta), blob_len), meta, *parts]))
+        return False
 
     def _run(self, group):
         while not self._evt_stop_thread.is_set():
+            t_wait = time.perf_counter()
             with self._queue_out.condition:
                 while self._queue_out.empty():
                     if self._evt_stop_thread.is_set():
@@ -275,15 +442,29 @@ class TensorSendThread(AbstractTensorExchangeThread):
                     self._queue_out.condition.wait()
                 payload = self._queue_out.get(block=False)
                 self._queue_out.condition.notify_all()
+            t_busy = time.perf_counter()
+            self.stats['wait_s'] += t_busy - t_wait
             data = payload.data
             is_tuple = isinstance(data, tuple)
             objs = data if is_tuple else (data,)
             tensors = [o for o in objs if isinstance(o, torch.Tensor)]
             cpu = [t for t in tensors if not t.is_cuda]
             cuda = [t for t in tensors if t.is_cuda]
-            self._send_envelope(_signature(objs, is_tuple), cpu)
+            hop = self._hop if cuda else None
+            fast = self._send_envelope(_signature(objs, is_tuple), cpu, defer_fast=hop is not None)
             self._call_pre_hooks()
-            if cuda:
+            if hop is not None:
+                # native fast path: envelope header + NCCL sends + event record in one GIL-free call
+                for tensor in cuda:
+                    tensor.record_stream(self._stream)
+                done = _fresh_event(self._stream)
+                hop.send(cuda, payload.ready, self._stream, done, write_envelope=fast)
+                if payload.on_consumed is not None:
+                    payload.on_consumed(done)
+                self._inflight.append(done)
+                while len(self._inflight) > 1 + queue_depth():
+                    self._inflight.popleft().synchronize()
+            elif cuda:
                 if group is None:
                     raise RuntimeError("CUDA tensors in a payload need the NCCL data plane (DistP2pContext with CUDA)")
                 with torch.cuda.stream(self._stream):
@@ -303,11 +484,13 @@ class TensorSendThread(AbstractTensorExchangeThread):
                     payload.on_consumed(done)
                 # bound the number of sends the host may run ahead of the device
                 self._inflight.append(done)
-                while len(self._inflight) > 2:
+                while len(self._inflight) > 1 + queue_depth():
                     self._inflight.popleft().synchronize()
             elif payload.on_consumed is not None:
                 payload.on_consumed(None)
             self._call_post_hooks(tuple(tensors))
+            self.stats['busy_s'] += time.perf_counter() - t_busy
+            self.stats['n'] += 1
 
 
 class TensorRecvThread(AbstractTensorExchangeThread):
@@ -318,7 +501,11 @@ class TensorRecvThread(AbstractTensorExchangeThread):
         self._queue_in = queue_in
         self._src_rank = src_rank
         self._sig = None
+        self._last_cpu: List[torch.Tensor] = []
+        self._conn = None
+        self._hop = None
         self._rings = {}
+        self._slots = ring_slots()
         self._count = 0
 
     def stop(self) -> None:
@@ -331,32 +518,56 @@ class TensorRecvThread(AbstractTensorExchangeThread):
         ring = self._rings.get(key)
         if ring is None:
             ring = [[torch.empty(shape, dtype=dtype, device=torch.device('cuda', self._device)), None]
-                    for _ in range(_RECV_SLOTS)]
+                    for _ in range(self._slots)]
             self._rings[key] = ring
-        return ring[self._count % _RECV_SLOTS]
+        return ring[self._count % self._slots]
 
     def run(self):
         """Receive payloads and enqueue them."""
         self._enter_device()
         group = DistP2pContext.hop_group(self._src_rank, dist.get_rank())
-        env = torch.zeros(_ENVELOPE, dtype=torch.uint8)
+        if self._conn is None:
+            self.open_hop()
+        conn, hop = self._conn, self._hop
+        try:
+            self._loop(conn, hop, group)
+        finally:
+            if hop is not None:
+                if self._stream is not None:
+                    self._stream.synchronize()
+                hop.close()
+            conn.close()
+
+    def open_hop(self) -> None:
+        """Accept the sender's connection and, on a GPU, join the hop's NCCL communicator."""
+        self._conn = DistP2pContext.accept_from(self._src_rank)
+        lib = _native_lib()
+        self._hop = _NativeHop(lib, self._conn, False) if lib is not None else None
+
+    def _loop(self, conn, hop, group):
         while True:
             # blocks until the sender's next payload or its closing envelope (sent by its shutdown); no polling
-            # thread per message as in the reference (`p2p/__init__.py:224-232`) - the closing handshake makes a
-            # plain blocking receive safe to shut down
-            try:
-                dist.recv(env, src=self._src_rank, tag=TAG_DATA_ENV)
-            except Exception:   # pylint: disable=broad-except
-                return          # the process group went away under us
-            meta_len, cpu_len = env[:16].view(torch.int64).tolist()
-            if meta_len < 0:
-                return   # the sender closed the hop
-            if meta_len + cpu_len <= _ENVELOPE - 16:
-                body = env[16:16 + meta_len + cpu_len].numpy().tobytes()
+            # thread per message as in the reference (`p2p/__init__.py:224-232`)
+            t_wait = time.perf_counter()
+            if hop is not None:
+                head = hop.wait_envelope()
+                t_busy = time.perf_counter()
+                self.stats['wait_s'] += t_busy - t_wait
+                if head is None:
+                    return      # the sender went away
+                meta_len, cpu_len = head
             else:
-                ext = torch.empty(meta_len + cpu_len, dtype=torch.uint8)
-                dist.recv(ext, src=self._src_rank, tag=TAG_DATA_EXT)
-                body = ext.numpy().tobytes()
+                head = _recv_exact(conn, _ENV_HEAD.size)
+                t_busy = time.perf_counter()
+                self.stats['wait_s'] += t_busy - t_wait
+                if not head:
+                    return      # the sender went away
+                meta_len, cpu_len = _ENV_HEAD.unpack(head)
+            if meta_len < 0:
+                return          # the sender closed the hop
+            reuse_cpu = cpu_len < 0
+            cpu_len = max(cpu_len, 0)
+            body = _recv_exact(conn, meta_len + cpu_len) if meta_len + cpu_len > 0 else b''
             if meta_len > 0:
                 self._sig = pickle.loads(body[:meta_len])
             sig = self._sig
@@ -364,23 +575,38 @@ class TensorRecvThread(AbstractTensorExchangeThread):
             objs: List[Any] = []
             cuda_slots = []
             off = meta_len
+            cpu_iter = iter(self._last_cpu) if reuse_cpu else None
+            new_cpu = []
             for pos, (plane, dtype, shape) in enumerate(sig[1:]):
                 if plane == 'obj':
                     objs.append(pickle.loads(dtype))
                 elif plane == 'cpu':
-                    tensor = torch.empty(shape, dtype=dtype)
-                    nbytes = tensor.numel() * tensor.element_size()
-                    if nbytes > 0:
-                        tensor.view(-1).view(torch.uint8).copy_(torch.frombuffer(bytearray(body[off:off + nbytes]), dtype=torch.uint8))
-                        off += nbytes
+                    if reuse_cpu:
+                        tensor = next(cpu_iter)   # read-only by contract: the same object is handed out again
+                    else:
+                        tensor = torch.empty(shape, dtype=dtype)
+                        nbytes = tensor.numel() * tensor.element_size()
+                        if nbytes > 0:
+                            tensor.view(-1).view(torch.uint8).copy_(torch.frombuffer(bytearray(body[off:off + nbytes]), dtype=torch.uint8))
+                            off += nbytes
+                        new_cpu.append(tensor)
                     objs.append(tensor)
                 else:
                     slot = self._slot(pos, dtype, shape)
                     cuda_slots.append(slot)
                     objs.append(slot[0])
+            if not reuse_cpu:
+                self._last_cpu = new_cpu
             ready = None
             on_consumed = None
-            if cuda_slots:
+            if cuda_slots and hop is not None:
+                ready = _fresh_event(self._stream)
+                hop.recv(cuda_slots, self._stream, ready)
+
+                def on_consumed(evt, slots=tuple(cuda_slots)):
+                    for slot in slots:
+                        slot[1] = evt
+            elif cuda_slots:
                 with torch.cuda.stream(self._stream):
                     for slot in cuda_slots:
                         if slot[1] is not None:
@@ -400,6 +626,8 @@ class TensorRecvThread(AbstractTensorExchangeThread):
             self._count += 1
             self._call_post_hooks(tuple(t for t in objs if isinstance(t, torch.Tensor)))
             data = tuple(objs) if sig[0] else objs[0]
+            self.stats['busy_s'] += time.perf_counter() - t_busy
+            self.stats['n'] += 1
             with self._queue_in.condition:
                 while self._queue_in.full():
                     if self._evt_stop_thread.is_set():
@@ -419,6 +647,7 @@ class TensorWorkThread(threading.Thread):
         self._callback = callback
         self._evt_stop_thread = threading.Event()
         self._device = torch.cuda.current_device() if torch.cuda.is_available() else None
+        self.stats = {'wait_s': 0.0, 'busy_s': 0.0, 'n': 0}
         self.exception: Optional[BaseException] = None
 
     def stop(self) -> None:
@@ -434,6 +663,7 @@ class TensorWorkThread(threading.Thread):
             torch.cuda.set_device(self._device)
             stream = torch.cuda.Stream(device=self._device)
         while True:
+            t_wait = time.perf_counter()
             with self._queue_in.condition:
                 while self._queue_in.empty():
                     if self._evt_stop_thread.is_set():
@@ -441,6 +671,8 @@ class TensorWorkThread(threading.Thread):
                     self._queue_in.condition.wait()
                 payload = self._queue_in.get(block=False)
                 self._queue_in.condition.notify_all()
+            t_busy = time.perf_counter()
+            self.stats['wait_s'] += t_busy - t_wait
             try:
                 if stream is not None:
                     with torch.cuda.stream(stream):
@@ -460,6 +692,8 @@ class TensorWorkThread(threading.Thread):
                 # the reference loses worker exceptions and hangs; keep it for the owner to re-raise
                 self.exception = exc
                 raise
+            self.stats['busy_s'] += time.perf_counter() - t_busy
+            self.stats['n'] += 1
             if result is not None and self._queue_out is not None:
                 with self._queue_out.condition:
                     while self._queue_out.full():
@@ -522,9 +756,10 @@ class DistP2pPipelineStage:
         self._create_stage(rank_src, rank_dst, work_cb, results_cb)
 
     def _create_stage(self, rank_src, rank_dst, work_cb, results_cb):
-        self._queues['in'] = ConditionQueue(maxsize=1)
-        self._queues['out'] = ConditionQueue(maxsize=1)
-        self._queues['res'] = ConditionQueue(maxsize=1)
+        depth = queue_depth()
+        self._queues['in'] = ConditionQueue(maxsize=depth)
+        self._queues['out'] = ConditionQueue(maxsize=depth)
+        self._queues['res'] = ConditionQueue(maxsize=depth)
         if work_cb is None:
             self._queues['out'] = self._queues['in']   # relay without a worker
         else:
@@ -542,6 +777,15 @@ class DistP2pPipelineStage:
         """Start the threads."""
         assert not self._initialized
         self._initialized = True
+        # Open this rank's hops in ascending order of the hop's SENDER rank before any thread runs. Opening blocks
+        # until the peer joins (socket accept, NCCL communicator init); a global order rules out circular waits.
+        hops = []
+        if 'send' in self._threads:
+            hops.append((dist.get_rank(), self._threads['send']))
+        if 'recv' in self._threads:
+            hops.append((self._threads['recv']._src_rank, self._threads['recv']))   # pylint: disable=protected-access
+        for _, thr in sorted(hops, key=lambda h: h[0]):
+            thr.open_hop()
         for thr in self._threads.values():
             thr.start()
 
@@ -587,6 +831,10 @@ class DistP2pPipelineStage:
 
     def __exit__(self, *args):
         self.shutdown()
+
+    def stats(self) -> dict:
+        """Per-thread host time: blocked waiting (`wait_s`) vs working (`busy_s`) and items handled."""
+        return {name: dict(thr.stats) for name, thr in self._threads.items() if hasattr(thr, 'stats')}
 
     def check_workers(self) -> None:
         """Re-raise an exception that killed a worker thread (the reference would hang instead)."""

@@ -30,6 +30,21 @@ def _passthrough_meta(items: int, item_shape: tuple):
     return meta
 
 
+_QUANT_META = {}
+
+
+def _quant_meta(items: int, item_shape: tuple, bit: int):
+    """Host-side `shape` (int32) and `quant_bit` (int8) tensors of an encoded payload: constant per (shape, bit),
+    so the same read-only objects are returned every time (the hop then skips re-sending them)."""
+    key = (items, item_shape, bit)
+    meta = _QUANT_META.get(key)
+    if meta is None:
+        meta = (torch.tensor(item_shape, dtype=torch.int32).expand(items, -1).clone(),
+                torch.full((items,), bit, dtype=torch.int8))
+        _QUANT_META[key] = meta
+    return meta
+
+
 def tensor_encode_outerdim(batched_tensor: torch.Tensor, quant_bit: int, clamp: bool = False) -> List[torch.Tensor]:
     """Per-item quantisation of a micro-batched fp32 CUDA tensor (`basic_op.py:166-170`).
 
@@ -40,8 +55,8 @@ def tensor_encode_outerdim(batched_tensor: torch.Tensor, quant_bit: int, clamp: 
     if quant_bit == 0:   # passthrough layout of `tensor_encode` (`basic_op.py:120-122`)
         return [batched_tensor, *_passthrough_meta(items, item_shape)]
     comm, scale, shift, _alpha = ops.quant_encode(batched_tensor, int(quant_bit), clamp)
-    shape = torch.tensor(item_shape, dtype=torch.int32).expand(items, -1).clone()
-    return [comm, shape, scale, shift, torch.full((items,), int(quant_bit), dtype=torch.int8)]
+    shape, bits = _quant_meta(items, item_shape, int(quant_bit))
+    return [comm, shape, scale, shift, bits]
 
 
 def tensor_decode_outerdim(batched_encodings: List[torch.Tensor]) -> torch.Tensor:

@@ -6,9 +6,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pipeedge_b200 import _lib, ops  # noqa: E402
 from pipeedge_b200._lib import LIB  # noqa: E402
 
-SHAPES = {'qkv': (1576, 2304, 768, _lib.PE_EPI_F16), 'out': (1576, 768, 768, _lib.PE_EPI_RESID_F32),
-          'fc1': (1576, 3072, 768, _lib.PE_EPI_GELU_F16), 'fc2': (1576, 768, 3072, _lib.PE_EPI_RESID_F32)}
-PLANS = {'qkv': ['1,1,256'], 'out': ['1,1,96'], 'fc1': ['1,1,256'], 'fc2': ['1,1,128']}
+SHAPES = {'qkv': (1576, 2304, 768, _lib.PE_EPI_F16), 'out': (1576, 768, 768, _lib.PE_EPI_F32),
+          'fc1': (1576, 3072, 768, _lib.PE_EPI_GELU_F16), 'fc2': (1576, 768, 3072, _lib.PE_EPI_F32)}
+PLANS = {'qkv': ['1,1,256'], 'out': ['1,1,96', '1,1,256'], 'fc1': ['1,1,256', '1,1,192'], 'fc2': ['1,1,128', '1,1,256']}
 MODES = ['0']   # bit0 no MMA, bit1 no TMA, bit3 no fence, bit4 plain arrive, bit5 no full wait
 trace = torch.zeros(148 * 12, dtype=torch.int64, device='cuda')
 for name, (m, n, k, epi) in SHAPES.items():
