@@ -217,8 +217,9 @@ int pe_hop_recv(pe_hop* hop, void* const* ptrs, const size_t* bytes, void* const
 int pe_debug_linear_simt(const void* a, const void* w, const void* bias, const void* resid, void* out, int m, int n,
                          int k, int epilogue, void* stream);
 
-/* While `buf` (device, >= 12 * 8 * grid bytes) is set, every pe_linear launch stores a per-CTA clock64 timeline
- * (start, setup done, first operands landed, last MMA issued, accumulator ready, epilogue done, exit). */
+/* While `buf` (device, >= 32 * 8 * grid bytes) is set, every pe_linear launch stores a per-CTA clock64 timeline
+ * (start, setup done, first operands landed, last MMA issued, accumulator ready, epilogue done, exit, epilogue and
+ * steady-state main-loop detail; 32 slots per CTA). */
 int pe_debug_gemm_trace(void* buf);
 
 #ifdef __cplusplus

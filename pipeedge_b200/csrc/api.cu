@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/pipeedge_b200.h"
 #include "common.cuh"
@@ -25,6 +26,15 @@ int check_cuda(cudaError_t err, const char* what) {
   set_error("CUDA error %d (%s) in %s", static_cast<int>(err), cudaGetErrorString(err), what);
   cudaGetLastError();  // consume it: a stale error must not be blamed on the next, unrelated call
   return PE_ERR_CUDA;
+}
+
+bool pdl_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("PE_NO_PDL");
+    cached = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return cached == 1;
 }
 
 void count_launches(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
@@ -51,7 +61,7 @@ int require_sm100() {
 
 int linear_impl(const void* a, const void* w, const void* bias, const void* resid, void* out, int m, int n, int k,
                 int epilogue, int rows_per_item, int out_item_rows, int out_row_offset, int resid_per_item,
-                cudaStream_t stream);
+                int static_w, cudaStream_t stream);
 int linear_simt_impl(const void* a, const void* w, const void* bias, const void* resid, void* out, int m, int n, int k,
                      int epilogue, cudaStream_t stream);
 int layernorm_impl(const void* x, const void* resid, const void* gamma, const void* beta, float eps, void* sum_out,
@@ -95,7 +105,8 @@ int pe_residual_layernorm(const void* y, const void* resid, const void* gamma, c
 
 int pe_linear(const void* a, const void* w, const void* bias, const void* resid, void* out, int m, int n, int k,
               int epilogue, void* stream) {
-  return pe::linear_impl(a, w, bias, resid, out, m, n, k, epilogue, 0, 0, 0, 0, static_cast<cudaStream_t>(stream));
+  return pe::linear_impl(a, w, bias, resid, out, m, n, k, epilogue, 0, 0, 0, 0, /*static_w=*/0,
+                         static_cast<cudaStream_t>(stream));
 }
 
 int pe_debug_linear_simt(const void* a, const void* w, const void* bias, const void* resid, void* out, int m, int n,

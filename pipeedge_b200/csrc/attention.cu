@@ -63,6 +63,8 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
 __global__ void __launch_bounds__(kAttnMaxWarps * 32)
 attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ ctx, int tokens, int heads, float scale_log2e) {
   extern __shared__ __align__(16) uint8_t attn_smem[];
+  pdl_launch_dependents();
+  pdl_wait();
   const int nwarps = blockDim.x >> 5;
   const int qrows = nwarps * 16;                          // query rows of this CTA
   const int kpad = (tokens + 15) & ~15;                   // keys rounded up to whole 16-key groups
@@ -261,9 +263,8 @@ int attention_impl(const void* qkv, void* ctx, int batch, int tokens, int heads,
   }
   const dim3 grid(splits, heads, batch);
   const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
-  attention_kernel<<<grid, warps * 32, smem, stream>>>(static_cast<const __half*>(qkv), static_cast<__half*>(ctx),
-                                                      tokens, heads, scale_log2e);
-  PE_CUDA(cudaGetLastError());
+  PE_CUDA(launch_pdl(attention_kernel, grid, dim3(warps * 32), smem, stream, static_cast<const __half*>(qkv),
+                     static_cast<__half*>(ctx), tokens, heads, scale_log2e));
   count_launches(1);
   return PE_OK;
 }

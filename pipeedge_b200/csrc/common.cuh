@@ -46,6 +46,34 @@ __device__ __forceinline__ float warp_max(float v) {
   return warp_reduce(v, [](float a, float b) { return fmaxf(a, b); });
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Every kernel of the stage path is launched with programmatic stream serialisation: it may become resident while
+// its predecessor is still draining, runs its private prologue (barrier init, TMEM alloc, descriptor prefetch) and then
+// blocks in pdl_wait() until the predecessor has completed and its writes are visible. Rules (stage.cu relies on them):
+// no global read of produced data and no global write before pdl_wait(); every PDL-launched kernel calls pdl_wait()
+// on every thread that touches global memory, so completion stays transitive along the stream.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();   // api.cu: on unless PE_NO_PDL=1
+
+// Launch `kernel` with the PDL attribute (when enabled) on `stream`.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -127,6 +155,30 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parit
       ::"r"(bar_addr), "r"(parity)
       : "memory");
 }
+// Both phases complete? The two try_waits are issued back to back, so their ~100-cycle result latencies overlap; a
+// miss (returns 0) falls back to mbar_wait_addr on each.
+__device__ __forceinline__ uint32_t mbar_try2_addr(uint32_t bar0, uint32_t parity0, uint32_t bar1, uint32_t parity1) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred q0, q1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 q0, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 q1, [%3], %4;\n\t"
+      "and.pred q0, q0, q1;\n\t"
+      "selp.u32 %0, 1, 0, q0;\n\t}"
+      : "=r"(ok)
+      : "r"(bar0), "r"(parity0), "r"(bar1), "r"(parity1)
+      : "memory");
+  return ok;
+}
+// Keeps a loop-invariant shared-memory address in a register: without it the compiler re-derives the address inside
+// the loop (S2UR SR_CgaCtaId + shifts for every use of a __shared__ symbol's shared-window address).
+__device__ __forceinline__ uint32_t keep_in_register(uint32_t x) {
+  asm volatile("mov.u32 %0, %0;" : "+r"(x));
+  return x;
+}
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx_addr(uint32_t bar_addr, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
 }
@@ -172,6 +224,12 @@ __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((
 constexpr uint32_t kUmmaDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
 
 // ---------------------------------------------------------------- TMA
+// Pull one box of a tensor into L2 without a shared-memory destination (weights ahead of their first use).
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }

@@ -13,7 +13,7 @@ void count_launches(int n);
 int require_sm100();
 int linear_impl(const void* a, const void* w, const void* bias, const void* resid, void* out, int m, int n, int k,
                 int epilogue, int rows_per_item, int out_item_rows, int out_row_offset, int resid_per_item,
-                cudaStream_t stream);
+                int static_w, cudaStream_t stream);
 
 // pixels f32 [B, C, img, img] -> patches f16 [B * np_side^2, kpad]; column = c*P*P + i*P + j (the flattened
 // Conv2d weight order), zero-padded up to kpad.
@@ -136,7 +136,7 @@ int pe_patch_embed(const void* pixels, const void* w, const void* bias, const vo
   count_launches(2);
   // out[b, n_prefix + p, :] = patches[b*np + p, :] @ w^T + bias + pos[n_prefix + p, :]
   return linear_impl(patches_work, w, bias, pos, out, batch * np, hidden, kpad, PE_EPI_RESID_F32, np, tokens, n_prefix, 1,
-                     stream);
+                     /*static_w=*/0, stream);
 }
 
 int pe_bert_embed(const void* ids, const void* pos_ids, const void* word, const void* type0, const void* pos,

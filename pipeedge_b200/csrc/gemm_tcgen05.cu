@@ -41,10 +41,12 @@ constexpr int kUmmaK = 16;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
 constexpr int kNumEpiWarps = 16;   // 4 TMEM lane quarters x 4 column groups: the epilogue is issue-latency bound
-constexpr int kGemmThreads = (2 + kNumEpiWarps) * 32;
-constexpr int kProducerWarp = kNumEpiWarps;      // warp 16
+constexpr int kGemmThreads = (3 + kNumEpiWarps) * 32;
+constexpr int kProducerWarp = kNumEpiWarps;      // warp 16: activations (A) + arms the full barriers
 constexpr int kMmaWarp = kNumEpiWarps + 1;       // warp 17
+constexpr int kWeightWarp = kNumEpiWarps + 2;    // warp 18: weights (W); never needs the predecessor's data
 constexpr int kMaxStages = 8;
+constexpr int kTraceSlots = 32;   // pe_debug_gemm_trace: clock64 stamps per CTA
 constexpr int kPipeSmemBudget = 144 * 1024;   // operand ring; the epilogue staging (80 KiB) follows it
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
 
@@ -58,7 +60,7 @@ struct GemmParams {
   int num_m_blocks, num_n_blocks, num_k_blocks;
   long long* trace;                // debug: per-CTA clock64 timeline (8 slots) or nullptr
   int tma_store;                   // 1: epilogue stages 32-row boxes in swizzled smem and TMA-stores them
-  int debug_mode;                  // debug (wrong results!): 1 = skip MMAs, 2 = skip TMA loads, 3 = skip the A loads
+  int debug_mode;                  // debug (wrong results!): bit0 = skip the MMAs, bit1 = skip all TMA loads
   int cm, cn;                      // cluster shape: CM CTAs along M share a W tile, CN along N share an A tile
   int num_super_m, num_super_n;    // cluster-level tiles (CM*128 x CN*BN)
   // Optional output-row remap (patch embedding writes token rows 1.. of each item and adds a
@@ -67,6 +69,8 @@ struct GemmParams {
   int out_item_rows;   // output rows per item
   int out_row_offset;  // first output row of an item that GEMM row 0 maps to
   int resid_per_item;  // 1: resid is [out_item_rows, n] shared by all items
+  int stg_offset;      // byte offset of the epilogue staging from the ring base: 0 = aliases the ring (one tile per CTA)
+  int static_w;        // 1: W is not written by anything still pending on the stream -> may be read before pdl_wait()
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -220,8 +224,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  long long* trace = p.trace != nullptr ? p.trace + static_cast<size_t>(blockIdx.x) * 12 : nullptr;
+  long long* trace = p.trace != nullptr ? p.trace + static_cast<size_t>(blockIdx.x) * kTraceSlots : nullptr;
   if (trace != nullptr && threadIdx.x == 0) trace[0] = clock64();
+  pdl_launch_dependents();   // the next kernel may become resident as SMs free up; it blocks in its own pdl_wait()
   // SWIZZLE_128B tiles must start on 1024-byte boundaries
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -259,6 +264,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   if (csize > 1) cluster_sync_all();   // peers must not multicast into barriers that are not initialised yet
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  // Everything above touched only this CTA's shared memory / TMEM and kernel parameters. The predecessor's output
+  // (A via TMA, resid) may be read, and buffers it may still be reading overwritten, only after pdl_wait(): the
+  // producer warp first pulls in what does NOT depend on the predecessor (the weights), everyone else waits here.
+  if (warp != kWeightWarp || p.static_w == 0) pdl_wait();
   if (trace != nullptr && threadIdx.x == 0) trace[1] = clock64();
   const int num_supers = p.num_super_m * p.num_super_n;
   const int cluster_id = static_cast<int>(blockIdx.x) / csize;
@@ -266,32 +275,106 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   const int a_slice_rows = kBlockM / p.cn;       // my share of the A tile
   const int b_slice_rows = p.block_n / p.cm;     // my share of the W tile
 
-  const uint32_t full_addr0 = smem_u32(&full_bar[0]);
-  const uint32_t empty_addr0 = smem_u32(&empty_bar[0]);
+  const uint32_t full_addr0 = keep_in_register(smem_u32(&full_bar[0]));
+  const uint32_t empty_addr0 = keep_in_register(smem_u32(&empty_bar[0]));
   const int num_k_blocks = p.num_k_blocks, num_stages = p.stages;
+  const bool pair_ok = num_stages >= 4;   // pairing needs two free stages per trip: with a 3-deep ring it starves the pipe
+  const int dbg = p.debug_mode;
+  // The three single-issuer loops below (A loads, W loads, MMA) are latency chains: barrier wait -> elect -> issue ->
+  // loop. Measured per k-block (profiles/r01d_gemm_loops.txt): a wait costs ~100-170 cycles even when the phase is
+  // already complete, expect_tx + two TMA issues ~200, four MMAs ~80, commit ~95, loop-back ~150: ~450 in all, more
+  // than the tensor time of a 128 x 96..160 tile (2*BN cycles). Hence A and W are issued from different warps, and
+  // every loop handles TWO k-blocks per trip: both barrier waits are issued back to back (latencies overlap) and one
+  // elected region issues both k-blocks' work.
   if (warp == kProducerWarp) {
-    // ---------------------------------------------------------------- TMA producer (warp converged, one lane issues)
-    const int cm = p.cm, cn = p.cn, nsm = p.num_super_m, bn = p.block_n;
+    // ---------------------------------------------------------------- A producer (warp converged, one lane issues)
+    const int cm = p.cm, cn = p.cn, nsm = p.num_super_m;
     const uint32_t a_off = static_cast<uint32_t>(n_rank * a_slice_rows) * (kBlockK * 2);
-    const uint32_t b_off = kABytes + static_cast<uint32_t>(m_rank * b_slice_rows) * (kBlockK * 2);
     int stage = 0;
     uint32_t phase = 0;
     for (int sup = cluster_id; sup < num_supers; sup += num_clusters) {
       const int a_row = ((sup % nsm) * cm + m_rank) * kBlockM + n_rank * a_slice_rows;
-      const int b_row = ((sup / nsm) * cn + n_rank) * bn + m_rank * b_slice_rows;
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
-        const uint32_t full_addr = full_addr0 + static_cast<uint32_t>(stage) * 8u;
-        mbar_wait_addr(empty_addr0 + static_cast<uint32_t>(stage) * 8u, phase ^ 1u);   // all my destinations drained it
+      for (int kb = 0; kb < num_k_blocks;) {
+        const bool two = pair_ok && kb + 1 < num_k_blocks;
+        int stage1 = stage + 1;
+        uint32_t phase1 = phase;
+        if (stage1 == num_stages) { stage1 = 0; phase1 ^= 1u; }
+        const uint32_t e0 = empty_addr0 + static_cast<uint32_t>(stage) * 8u;
+        const uint32_t e1 = empty_addr0 + static_cast<uint32_t>(stage1) * 8u;
+        // all my destinations drained the stage(s)
+        if (!two) mbar_wait_addr(e0, phase ^ 1u);
+        else if (!mbar_try2_addr(e0, phase ^ 1u, e1, phase1 ^ 1u)) { mbar_wait_addr(e0, phase ^ 1u); mbar_wait_addr(e1, phase1 ^ 1u); }
         if (elect_one()) {
-          const uint32_t sa = smem_base + static_cast<uint32_t>(stage) * stage_bytes;
-          mbar_arrive_expect_tx_addr(full_addr, stage_bytes);
-          if (cn > 1) tma_load_2d_multicast_addr(sa + a_off, &tm_a, full_addr, kb * kBlockK, a_row, row_mask);
-          else tma_load_2d_addr(sa + a_off, &tm_a, full_addr, kb * kBlockK, a_row);
-          if (cm > 1) tma_load_2d_multicast_addr(sa + b_off, &tm_b, full_addr, kb * kBlockK, b_row, col_mask);
-          else tma_load_2d_addr(sa + b_off, &tm_b, full_addr, kb * kBlockK, b_row);
+          const uint32_t f0 = full_addr0 + static_cast<uint32_t>(stage) * 8u;
+          const uint32_t sa0 = smem_base + static_cast<uint32_t>(stage) * stage_bytes + a_off;
+          if (dbg & 2) mbar_arrive_addr(f0);                     // debug: no loads at all, operands are garbage
+          else {
+          mbar_arrive_expect_tx_addr(f0, stage_bytes);           // A and W bytes; W's complete_tx may already be in
+          if (cn > 1) tma_load_2d_multicast_addr(sa0, &tm_a, f0, kb * kBlockK, a_row, row_mask);
+          else tma_load_2d_addr(sa0, &tm_a, f0, kb * kBlockK, a_row);
+          }
+          if (two) {
+            const uint32_t f1 = full_addr0 + static_cast<uint32_t>(stage1) * 8u;
+            const uint32_t sa1 = smem_base + static_cast<uint32_t>(stage1) * stage_bytes + a_off;
+            if (dbg & 2) mbar_arrive_addr(f1);
+            else {
+            mbar_arrive_expect_tx_addr(f1, stage_bytes);
+            if (cn > 1) tma_load_2d_multicast_addr(sa1, &tm_a, f1, (kb + 1) * kBlockK, a_row, row_mask);
+            else tma_load_2d_addr(sa1, &tm_a, f1, (kb + 1) * kBlockK, a_row);
+            }
+          }
         }
         __syncwarp();
+        if (two) { stage = stage1; phase = phase1; }
         if (++stage == num_stages) { stage = 0; phase ^= 1u; }
+        kb += two ? 2 : 1;
+      }
+    }
+  } else if (warp == kWeightWarp) {
+    // ---------------------------------------------------------------- W producer (warp converged, one lane issues)
+    const int cm = p.cm, cn = p.cn, nsm = p.num_super_m, bn = p.block_n;
+    const uint32_t b_off = kABytes + static_cast<uint32_t>(m_rank * b_slice_rows) * (kBlockK * 2);
+    // Static weights do not depend on the predecessor kernel: this warp skipped pdl_wait(), so while the predecessor
+    // drains it already streams the first stages' weights into shared memory and pulls the rest of its weight panel
+    // into L2 (shared out among the CTAs that read the same panel).
+    if (p.static_w != 0 && cluster_id < num_supers && elect_one()) {
+      const int b_row = ((cluster_id / nsm) * cn + n_rank) * bn + m_rank * b_slice_rows;
+      const int sharers = nsm * cm;
+      const int me = (cluster_id % nsm) * cm + m_rank;
+      for (int kb = num_stages + me; kb < num_k_blocks; kb += sharers) tma_prefetch_l2_2d(&tm_b, kb * kBlockK, b_row);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int sup = cluster_id; sup < num_supers; sup += num_clusters) {
+      const int b_row = ((sup / nsm) * cn + n_rank) * bn + m_rank * b_slice_rows;
+      for (int kb = 0; kb < num_k_blocks;) {
+        const bool two = pair_ok && kb + 1 < num_k_blocks;
+        int stage1 = stage + 1;
+        uint32_t phase1 = phase;
+        if (stage1 == num_stages) { stage1 = 0; phase1 ^= 1u; }
+        const uint32_t e0 = empty_addr0 + static_cast<uint32_t>(stage) * 8u;
+        const uint32_t e1 = empty_addr0 + static_cast<uint32_t>(stage1) * 8u;
+        if (!two) mbar_wait_addr(e0, phase ^ 1u);
+        else if (!mbar_try2_addr(e0, phase ^ 1u, e1, phase1 ^ 1u)) { mbar_wait_addr(e0, phase ^ 1u); mbar_wait_addr(e1, phase1 ^ 1u); }
+        if (elect_one()) {
+          const uint32_t f0 = full_addr0 + static_cast<uint32_t>(stage) * 8u;
+          const uint32_t sb0 = smem_base + static_cast<uint32_t>(stage) * stage_bytes + b_off;
+          if (dbg & 2) {}
+          else if (cm > 1) tma_load_2d_multicast_addr(sb0, &tm_b, f0, kb * kBlockK, b_row, col_mask);
+          else tma_load_2d_addr(sb0, &tm_b, f0, kb * kBlockK, b_row);
+          if (two) {
+            const uint32_t f1 = full_addr0 + static_cast<uint32_t>(stage1) * 8u;
+            const uint32_t sb1 = smem_base + static_cast<uint32_t>(stage1) * stage_bytes + b_off;
+            if (dbg & 2) {}
+            else if (cm > 1) tma_load_2d_multicast_addr(sb1, &tm_b, f1, (kb + 1) * kBlockK, b_row, col_mask);
+            else tma_load_2d_addr(sb1, &tm_b, f1, (kb + 1) * kBlockK, b_row);
+          }
+        }
+        __syncwarp();
+        if (two) { stage = stage1; phase = phase1; }
+        if (++stage == num_stages) { stage = 0; phase ^= 1u; }
+        kb += two ? 2 : 1;
       }
     }
   } else if (warp == kMmaWarp) {
@@ -299,7 +382,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     const uint32_t idesc = umma_idesc_f16(kBlockM, p.block_n);
     const uint32_t a_lo0 = umma_desc_lo(smem_base);
     const uint32_t stage_lo = stage_bytes >> 4;
-    const uint32_t tmem_full_addr0 = smem_u32(&tmem_full_bar[0]);
+    const uint32_t tmem_full_addr0 = keep_in_register(smem_u32(&tmem_full_bar[0]));
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -308,26 +391,49 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
       tcgen05_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccStride);
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
-        mbar_wait_addr(full_addr0 + static_cast<uint32_t>(stage) * 8u, phase);
+      for (int kb = 0; kb < num_k_blocks;) {
+        const bool two = pair_ok && kb + 1 < num_k_blocks;
+        int stage1 = stage + 1;
+        uint32_t phase1 = phase;
+        if (stage1 == num_stages) { stage1 = 0; phase1 ^= 1u; }
+        const uint32_t f0 = full_addr0 + static_cast<uint32_t>(stage) * 8u;
+        const uint32_t f1 = full_addr0 + static_cast<uint32_t>(stage1) * 8u;
+        if (!two) mbar_wait_addr(f0, phase);
+        else if (!mbar_try2_addr(f0, phase, f1, phase1)) { mbar_wait_addr(f0, phase); mbar_wait_addr(f1, phase1); }
         tcgen05_fence_after();
         if (trace != nullptr && sup == cluster_id && kb == 0 && lane == 0) trace[2] = clock64();
         if (elect_one()) {
           const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(stage) * stage_lo;
           const uint32_t b_lo = a_lo + (kABytes >> 4);
+          if (!(dbg & 1)) {
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // advancing K by 16 fp16 = 32 bytes inside the swizzled row: +2 in 16-byte units
             umma_f16_ss_lohi(d_tmem, a_lo + k * 2, b_lo + k * 2, kUmmaDescHiSw128, idesc, (kb | k) != 0 ? 1u : 0u);
           }
+          }
           // release the stage to every CTA that wrote part of it (incl. this one)
-          const uint32_t empty_addr = empty_addr0 + static_cast<uint32_t>(stage) * 8u;
-          if (csize > 1) umma_commit_multicast_addr(empty_addr, peers_mask);
-          else umma_commit_addr(empty_addr);
-          if (kb == num_k_blocks - 1) umma_commit_addr(tmem_full_addr0 + static_cast<uint32_t>(acc) * 8u);
+          const uint32_t e0 = empty_addr0 + static_cast<uint32_t>(stage) * 8u;
+          if (csize > 1) umma_commit_multicast_addr(e0, peers_mask);
+          else umma_commit_addr(e0);
+          if (two) {
+            const uint32_t a_lo1 = a_lo0 + static_cast<uint32_t>(stage1) * stage_lo;
+            const uint32_t b_lo1 = a_lo1 + (kABytes >> 4);
+            if (!(dbg & 1)) {
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_f16_ss_lohi(d_tmem, a_lo1 + k * 2, b_lo1 + k * 2, kUmmaDescHiSw128, idesc, 1u);
+            }
+            const uint32_t e1 = empty_addr0 + static_cast<uint32_t>(stage1) * 8u;
+            if (csize > 1) umma_commit_multicast_addr(e1, peers_mask);
+            else umma_commit_addr(e1);
+          }
+          if (kb + (two ? 2 : 1) >= num_k_blocks) umma_commit_addr(tmem_full_addr0 + static_cast<uint32_t>(acc) * 8u);
         }
         __syncwarp();
+        if (two) { stage = stage1; phase = phase1; }
         if (++stage == num_stages) { stage = 0; phase ^= 1u; }
+        kb += two ? 2 : 1;
       }
       if (trace != nullptr && sup == cluster_id && lane == 0) trace[3] = clock64();
       acc ^= 1;
@@ -338,7 +444,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     const int quarter = warp & 3;          // TMEM lanes [32*quarter, 32*quarter+32) are this warp's
     const int group = warp >> 2;           // 32-column chunks c = group, group + 4, ... are this warp's
     const int chunks = p.block_n >> 5;     // block_n is a multiple of 32
-    float* stg = reinterpret_cast<float*>(smem_gen + static_cast<size_t>(p.stages) * stage_bytes) + warp * kStgFloatsPerWarp;
+    float* stg = reinterpret_cast<float*>(smem_gen + p.stg_offset) + warp * kStgFloatsPerWarp;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int sup = cluster_id; sup < num_supers; sup += num_clusters) {
@@ -351,64 +457,58 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(acc * kAccStride);
       if (p.tma_store) {
-        // ---- TMEM -> registers -> (bias, activation, convert) -> 128B-swizzled shared box -> TMA store.
-        // One box = this warp's 32 rows x 128 bytes (64 fp16 or 32 fp32 columns); TMA clips the M / N tails.
+        // ---- TMEM -> registers -> (bias, activation, convert) -> swizzled shared box -> TMA store.
+        // One box = this warp's 32 rows x 32 columns: 64-byte rows (fp16, SWIZZLE_64B) or 128-byte rows (fp32,
+        // SWIZZLE_128B), so any block_n that is a multiple of 32 tiles exactly; TMA clips the M / N tails.
         constexpr bool kHalfOut = (EPI == PE_EPI_F16 || EPI == PE_EPI_GELU_F16);
-        constexpr int kBoxCols = kHalfOut ? 64 : 32;
-        const int boxes = (p.block_n + kBoxCols - 1) / kBoxCols;
-        uint8_t* box = reinterpret_cast<uint8_t*>(stg);            // 4 KiB, 1024-byte aligned
+        uint8_t* box = reinterpret_cast<uint8_t*>(stg);            // <= 4 KiB, 1024-byte aligned
         const uint32_t box_addr = smem_u32(box);
-        uint8_t* my_row = box + lane * 128;
-        const int sw = lane & 7;                                   // 16-byte chunk j of row r lives at j ^ (r & 7)
-        for (int bx = group; bx < boxes; bx += kNumEpiWarps / 4) {
-          const int col0 = n_blk * p.block_n + bx * kBoxCols;
+        uint8_t* my_row = box + lane * (kHalfOut ? 64 : 128);
+        // 16-byte chunk j of row r lives at j ^ (r & 7) (128B swizzle) or j ^ ((r >> 1) & 3) (64B swizzle)
+        const int sw = kHalfOut ? ((lane >> 1) & 3) : (lane & 7);
+        for (int c = group; c < chunks; c += kNumEpiWarps / 4) {
+          const int gcol = n_blk * p.block_n + c * 32;
           if (lane == 0) tma_store_wait_read();                    // the previous box has left shared memory
           __syncwarp();
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c * 32), r);
+          tmem_wait_ld();
+          float v[32];
 #pragma unroll
-          for (int hseg = 0; hseg < kBoxCols / 32; ++hseg) {
-            const int cbase = bx * kBoxCols + hseg * 32;           // column within the tile
-            if (cbase >= p.block_n) break;
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(cbase), r);
-            tmem_wait_ld();
-            float v[32];
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (p.bias != nullptr) {
+            if (gcol + 32 <= p.n) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-            const int gcol = n_blk * p.block_n + cbase;
-            if (p.bias != nullptr) {
-              if (gcol + 32 <= p.n) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol) + i);
-                  v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (gcol + i < p.n) v[i] += __ldg(p.bias + gcol + i);
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = epi_act<EPI>(v[i]);
-            if (kHalfOut) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {                        // 4 chunks of 8 halves
-                uint4 pk;
-                __half2* h2 = reinterpret_cast<__half2*>(&pk);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) h2[i] = __floats2half2_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
-                *reinterpret_cast<uint4*>(my_row + (((hseg * 4 + j) ^ sw) << 4)) = pk;
+              for (int i = 0; i < 8; ++i) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol) + i);
+                v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < 8; ++j)                          // 8 chunks of 4 floats
-                *reinterpret_cast<float4*>(my_row + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              for (int i = 0; i < 32; ++i)
+                if (gcol + i < p.n) v[i] += __ldg(p.bias + gcol + i);
             }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = epi_act<EPI>(v[i]);
+          if (kHalfOut) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {                          // 4 chunks of 8 halves
+              uint4 pk;
+              __half2* h2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) h2[i] = __floats2half2_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
+              *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) = pk;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)                            // 8 chunks of 4 floats
+              *reinterpret_cast<float4*>(my_row + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
           fence_proxy_async_smem();                                // generic-proxy writes -> visible to the TMA engine
           __syncwarp();
-          if (lane == 0 && row0 < p.m && col0 < p.n) {
-            tma_store_2d(&tm_out, box_addr, col0, row0);
+          if (lane == 0 && row0 < p.m && gcol < p.n) {
+            tma_store_2d(&tm_out, box_addr, gcol, row0);
             tma_store_commit();
           }
         }
@@ -499,10 +599,11 @@ static int encode_out_2d(CUtensorMap* map, void* ptr, uint64_t rows, uint64_t co
   if (fn == nullptr) return PE_ERR_CUDA;
   const cuuint64_t dims[2] = {cols, rows};
   const cuuint64_t strides[1] = {cols * (half_out ? 2u : 4u)};
-  const cuuint32_t box[2] = {half_out ? 64u : 32u, 32u};
+  const cuuint32_t box[2] = {32u, 32u};   // 64-byte (fp16) or 128-byte (fp32) rows
   const cuuint32_t estr[2] = {1, 1};
   const CUresult rc = fn(map, half_out ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims,
-                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         half_out ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled (output) failed (CUresult %d)", static_cast<int>(rc));
@@ -520,13 +621,16 @@ static int max_clusters(int csize) {
   return csize == 1 ? kNumSMs : (csize == 2 ? kNumSMs / 2 : 132 / csize);
 }
 
-// Cost model in SM cycles, fitted to per-CTA clock64 timelines measured on B200 (profiles/r01b_gemm_timeline.txt):
-//   set-up ~1200 (+800 for a cluster launch) and ~2000 until the first operands land;
-//   main loop: K/64 blocks, each max(2*BN tensor cycles, ~450 issue/latency floor);
-//   earlier waves' epilogues hide under the next tile's main loop; the last wave's is exposed and is the larger
-//   of its store burst (~1400 B/cycle chip-wide, every CTA stores at once) and the per-warp chunk latency.
-// Clusters (TMA multicast) cut L2 reads, but these shapes are not L2-bound, so they rarely win.
-GemmPlan plan_gemm(int m, int n, int k, int out_elem_bytes) {
+// Cost model in SM cycles, fitted on B200 to in-graph launch times of the ViT-B shapes under forced plans with weights
+// streaming from HBM (profiles/r01d_plan_sweep.txt; +-1k cycles over 24 shape x plan points):
+//   fixed ~7000: launch gap, set-up, first operands landing, drain;
+//   main loop: K/64 blocks of ~(415 + BN) cycles each - a per-block issue/latency cost plus the tile's shared-memory
+//     ingest, NOT the 2*BN tensor cycles: one CTA per SM cannot keep tcgen05 busy at these tile sizes;
+//   epilogue of a 128 x BN tile ~1200 + c*BN, c = 6 (fp16), 8 (fp32), 24 (fp16 + erf GELU: MUFU / issue bound);
+//   tiles are dealt round-robin to <=148 CTAs: a CTA with r tiles hides each epilogue but the last under the next
+//     tile's main loop (two TMEM accumulators), unless the epilogue is the longer of the two.
+// Clusters (TMA multicast) cut L2 reads, but these shapes are not L2-bound: they only pay the cluster launch cost.
+GemmPlan plan_gemm(int m, int n, int k, int epilogue) {
   int forced[3] = {0, 0, 0};
   const char* env = getenv("PE_GEMM_FORCE");   // "CM,CN,BN": tuning / debugging only
   if (env != nullptr && sscanf(env, "%d,%d,%d", &forced[0], &forced[1], &forced[2]) == 3 && forced[0] > 0)
@@ -535,22 +639,19 @@ GemmPlan plan_gemm(int m, int n, int k, int out_elem_bytes) {
   double best_cost = 1e30;
   const int shapes[4][2] = {{1, 1}, {2, 1}, {1, 2}, {2, 2}};
   const double kb = (k + kBlockK - 1) / kBlockK;
+  const double epi_per_col = epilogue == PE_EPI_GELU_F16 ? 24.0 : (epilogue == PE_EPI_F16 ? 6.0 : (epilogue == PE_EPI_TANH_F32 ? 30.0 : 8.0));
   for (const auto& sh : shapes) {
     const int cm = sh[0], cn = sh[1], csize = cm * cn;
     for (int bn = 256; bn >= 32; bn -= 32) {
       if ((bn / cm) % 8 != 0 || (bn % cm) != 0) continue;   // W slices must keep whole 8-row swizzle atoms
-      if (out_elem_bytes == 2 && (bn % 64) != 0) continue;  // fp16 TMA-store boxes are 64 columns wide
       const long sm_ = (m + kBlockM * cm - 1) / (kBlockM * cm);
       const long sn_ = (n + bn * cn - 1) / (bn * cn);
       const long supers = sm_ * sn_;
       const long avail = max_clusters(csize);
-      const long waves = (supers + avail - 1) / avail;
-      const double per_kb = 2.0 * bn > 450.0 ? 2.0 * bn : 450.0;
-      const double last_tiles = static_cast<double>(supers - (waves - 1) * avail) * csize;
-      const double burst = last_tiles * kBlockM * bn * out_elem_bytes / 1400.0;
-      const double lat = ((bn / 32 + 3) / 4) * (out_elem_bytes == 2 ? 1300.0 : 1500.0);
-      const double cost = 1200.0 + (csize > 1 ? 800.0 : 0.0) + 2000.0 + waves * kb * per_kb +
-                          (burst > lat ? burst : lat) + 500.0;
+      const long rounds = (supers + avail - 1) / avail;       // tiles of the busiest CTA
+      const double loop = kb * (415.0 + bn);
+      const double epi = 1200.0 + epi_per_col * bn;
+      const double cost = 7000.0 + (csize > 1 ? 800.0 : 0.0) + loop + (rounds - 1) * (loop > epi ? loop : epi) + epi;
       if (cost < best_cost - 1e-9) {
         best_cost = cost;
         best = {cm, cn, bn};
@@ -571,7 +672,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     configured = true;
   }
   const uint32_t stage_bytes = kABytes + static_cast<uint32_t>(p.block_n) * (kBlockK * 2);
-  const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + kStgBytes + 1024;
+  const size_t ring = static_cast<size_t>(p.stages) * stage_bytes, stg_end = static_cast<size_t>(p.stg_offset) + kStgBytes;
+  const size_t smem = (ring > stg_end ? ring : stg_end) + 1024;
   const int csize = p.cm * p.cn;
   const int supers = p.num_super_m * p.num_super_n;
   const int avail = max_clusters(csize);
@@ -581,13 +683,15 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = static_cast<unsigned>(csize);
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   PE_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<EPI>, ta, tb, tout, p));
   count_launches(1);
   return PE_OK;
@@ -595,7 +699,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
 
 int linear_impl(const void* a, const void* w, const void* bias, const void* resid, void* out, int m, int n, int k,
                 int epilogue, int rows_per_item, int out_item_rows, int out_row_offset, int resid_per_item,
-                cudaStream_t stream) {
+                int static_w, cudaStream_t stream) {
   PE_REQUIRE(a && w && out, "pe_linear: null pointer");
   PE_REQUIRE(m > 0 && n > 0 && k > 0, "pe_linear: bad shape m=%d n=%d k=%d", m, n, k);
   PE_REQUIRE((k & 7) == 0, "pe_linear: k=%d must be a multiple of 8 (16-byte TMA row pitch)", k);
@@ -605,7 +709,7 @@ int linear_impl(const void* a, const void* w, const void* bias, const void* resi
   int rc = require_sm100();
   if (rc != PE_OK) return rc;
 
-  const GemmPlan plan = plan_gemm(m, n, k, (epilogue == PE_EPI_F16 || epilogue == PE_EPI_GELU_F16) ? 2 : 4);
+  const GemmPlan plan = plan_gemm(m, n, k, epilogue);
   PE_REQUIRE(plan.bn >= 32 && plan.bn <= 256 && plan.bn % 32 == 0 && plan.cm >= 1 && plan.cn >= 1 &&
                  plan.cm * plan.cn <= 8 && kBlockM % plan.cn == 0 && (plan.bn / plan.cm) % 8 == 0,
              "pe_linear: bad tile plan cm=%d cn=%d bn=%d", plan.cm, plan.cn, plan.bn);
@@ -619,19 +723,30 @@ int linear_impl(const void* a, const void* w, const void* bias, const void* resi
   p.cm = plan.cm;
   p.cn = plan.cn;
   const uint32_t stage_bytes = kABytes + static_cast<uint32_t>(p.block_n) * (kBlockK * 2);
-  int stages = kPipeSmemBudget / static_cast<int>(stage_bytes);
-  p.stages = stages > kMaxStages ? kMaxStages : (stages < 2 ? 2 : stages);
   p.num_m_blocks = (m + kBlockM - 1) / kBlockM;
   p.num_n_blocks = (n + p.block_n - 1) / p.block_n;
-  p.num_k_blocks = (k + kBlockK - 1) / kBlockK;
   p.num_super_m = (p.num_m_blocks + p.cm - 1) / p.cm;
   p.num_super_n = (p.num_n_blocks + p.cn - 1) / p.cn;
+  // One tile per CTA: the epilogue starts only after the last MMA has read the ring, so its staging may alias the
+  // ring and the whole 224 KiB go to pipeline depth (BN=256: 4 stages instead of 3). With several tiles per CTA the
+  // next tile's loads overlap the epilogue and the two need separate space.
+  const bool one_round = p.num_super_m * p.num_super_n <= max_clusters(p.cm * p.cn);
+  int stages = (one_round ? kPipeSmemBudget + kStgBytes : kPipeSmemBudget) / static_cast<int>(stage_bytes);
+  p.stages = stages > kMaxStages ? kMaxStages : (stages < 2 ? 2 : stages);
+  if (const char* cap = getenv("PE_GEMM_STAGES")) {   // tuning scripts only
+    const int c = atoi(cap);
+    if (c >= 2 && c < p.stages) p.stages = c;
+  }
+  p.stg_offset = one_round ? 0 : p.stages * static_cast<int>(stage_bytes);
+  p.num_k_blocks = (k + kBlockK - 1) / kBlockK;
   p.trace = g_gemm_trace;
   p.debug_mode = 0;
+  if (const char* dm = getenv("PE_GEMM_DEBUG_MODE")) p.debug_mode = atoi(dm);   // timing experiments only: results are wrong
   p.rows_per_item = rows_per_item;
   p.out_item_rows = out_item_rows;
   p.out_row_offset = out_row_offset;
   p.resid_per_item = resid_per_item;
+  p.static_w = (static_w != 0 || getenv("PE_GEMM_STATIC_W") != nullptr) ? 1 : 0;   // env: tuning scripts only
 
   CUtensorMap ta, tb;   // each CTA loads its SLICE of a tile: 128/CN rows of A, BN/CM rows of W
   rc = encode_f16_2d(&ta, a, static_cast<uint64_t>(m), static_cast<uint64_t>(k), static_cast<uint32_t>(kBlockM / p.cn));
@@ -646,7 +761,6 @@ int linear_impl(const void* a, const void* w, const void* bias, const void* resi
   p.tma_store = (epilogue != PE_EPI_RESID_F32 && rows_per_item == 0 && (out_pitch & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
   if (getenv("PE_GEMM_NO_TMA_STORE") != nullptr) p.tma_store = 0;
-  if (half_out && (p.block_n % 64) != 0) p.tma_store = 0;   // a box must not spill into the next tile's columns
   if (p.tma_store) {
     rc = encode_out_2d(&tout, out, static_cast<uint64_t>(m), static_cast<uint64_t>(n), half_out);
     if (rc != PE_OK) return rc;

@@ -25,6 +25,8 @@ __global__ void __launch_bounds__(kLnWarpsPerBlock * 32)
 layernorm_kernel(const float* __restrict__ x, const float* resid, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, float* sum_out, float* out_f32, __half* out_f16, int rows,
                  int hidden) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * kLnWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -90,11 +92,10 @@ int layernorm_impl(const void* x, const void* resid, const void* gamma, const vo
   const int grid = (rows + kLnWarpsPerBlock - 1) / kLnWarpsPerBlock;
   static bool configured = false;
   if (!configured) { prefer_max_shared(layernorm_kernel); configured = true; }
-  layernorm_kernel<<<grid, kLnWarpsPerBlock * 32, 0, stream>>>(
-      static_cast<const float*>(x), static_cast<const float*>(resid), static_cast<const float*>(gamma),
-      static_cast<const float*>(beta), eps, static_cast<float*>(sum_out), static_cast<float*>(out_f32),
-      static_cast<__half*>(out_f16), rows, hidden);
-  PE_CUDA(cudaGetLastError());
+  PE_CUDA(launch_pdl(layernorm_kernel, dim3(grid), dim3(kLnWarpsPerBlock * 32), 0, stream,
+                     static_cast<const float*>(x), static_cast<const float*>(resid), static_cast<const float*>(gamma),
+                     static_cast<const float*>(beta), eps, static_cast<float*>(sum_out), static_cast<float*>(out_f32),
+                     static_cast<__half*>(out_f16), rows, hidden));
   count_launches(1);
   return PE_OK;
 }

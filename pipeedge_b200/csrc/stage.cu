@@ -24,7 +24,7 @@ void count_launches(int n);
 int require_sm100();
 int linear_impl(const void* a, const void* w, const void* bias, const void* resid, void* out, int m, int n, int k,
                 int epilogue, int rows_per_item, int out_item_rows, int out_row_offset, int resid_per_item,
-                cudaStream_t stream);
+                int static_w, cudaStream_t stream);
 int layernorm_impl(const void* x, const void* resid, const void* gamma, const void* beta, float eps, void* sum_out,
                    void* out_f32, void* out_f16, int rows, int hidden, cudaStream_t stream);
 int add_impl(const void* a, const void* b, void* out, size_t n, cudaStream_t stream);
@@ -91,7 +91,7 @@ static int prof_mark(Prof* prof, int kind) {
 
 static int lin(const void* a, const void* w, const void* b, const void* resid, void* out, int m, int n, int k, int epi,
                cudaStream_t s) {
-  return linear_impl(a, w, b, resid, out, m, n, k, epi, 0, 0, 0, 0, s);
+  return linear_impl(a, w, b, resid, out, m, n, k, epi, 0, 0, 0, 0, /*static_w=*/1, s);
 }
 
 // Enqueue the kernel sequence of one forward on `stream`. Returns the number of kernels in *count.

@@ -8,9 +8,12 @@ from pipeedge_b200._lib import LIB  # noqa: E402
 
 SHAPES = {'qkv': (1576, 2304, 768, _lib.PE_EPI_F16), 'out': (1576, 768, 768, _lib.PE_EPI_F32),
           'fc1': (1576, 3072, 768, _lib.PE_EPI_GELU_F16), 'fc2': (1576, 768, 3072, _lib.PE_EPI_F32)}
-PLANS = {'qkv': ['1,1,256'], 'out': ['1,1,96', '1,1,256'], 'fc1': ['1,1,256', '1,1,192'], 'fc2': ['1,1,128', '1,1,256']}
-MODES = ['0']   # bit0 no MMA, bit1 no TMA, bit3 no fence, bit4 plain arrive, bit5 no full wait
-trace = torch.zeros(148 * 12, dtype=torch.int64, device='cuda')
+PLANS = {'qkv': ['1,1,224'], 'out': ['1,1,96'], 'fc1': ['1,1,160', '1,1,256'], 'fc2': ['1,1,96', '1,1,256']}
+if os.environ.get('TRACE_ONLY'):
+    SHAPES = {k: v for k, v in SHAPES.items() if k in os.environ['TRACE_ONLY'].split(',')}
+MODES = os.environ.get('TRACE_MODES', '0').split(',')   # bit0 no MMA, bit1 no TMA, bit3 no fence, bit4 plain arrive, bit5 no full wait
+SLOTS = 32
+trace = torch.zeros(148 * SLOTS, dtype=torch.int64, device='cuda')
 for name, (m, n, k, epi) in SHAPES.items():
     a = torch.randn(m, k, device='cuda').half()
     w = torch.randn(n, k, device='cuda').half() * 0.05
@@ -30,10 +33,10 @@ for name, (m, n, k, epi) in SHAPES.items():
         e.record()
         torch.cuda.synchronize()
         LIB.pe_debug_gemm_trace(None)
-        t = trace.view(148, 12).cpu()
+        t = trace.view(148, SLOTS).cpu()
         used = t[:, 0] > 0
         t = t[used]
-        rel = t[:, :10] - t[:, :1]     # clock64 is per SM: only differences within a CTA mean anything (int64 maths)
-        names = ['start', 'setup', 'first_full', 'mma_issued', 'acc_ready', 'epi_done', 'exit', 'ld1', 'sts1', 'chunk1']
+        rel = t[:, :7] - t[:, :1]     # clock64 is per SM: only differences within a CTA mean anything (int64 maths)
+        names = ['start', 'setup', 'first_full', 'mma_issued', 'acc_ready', 'epi_done', 'exit']
         print(f"{name} plan {plan} mode {mode}: mainloop med {int((t[:, 3] - t[:, 2]).median())} cycles; ctas {int(used.sum())} event_us {s.elapsed_time(e) * 1e3:.1f}")
         print("   " + "  ".join(f"{nm}: med {int(rel[:, i].median())} max {int(rel[:, i].max())}" for i, nm in enumerate(names)))
