@@ -21,6 +21,7 @@ One JSON line is printed by rank 0:
 the GPU box).
 """
 import argparse
+import faulthandler
 import json
 import os
 import statistics
@@ -354,8 +355,11 @@ def run_single_gpu(args, spec, ubatch, seq, qbit, metric, unit, workload):
 def run_pipeline(args, spec, ubatch, seq, qbit, metric, unit, workload):
     """N > 1: one stage per rank through DistP2pContext / DistP2pPipelineStage (the runtime.py path)."""
     import torch.distributed as dist
+    # hand-off queues three deep (the reference's are one deep): more micro-batches in flight hide the host-side
+    # hand-offs between the per-stage threads; results are unchanged (tests/test_pipeline_gpu.py)
+    os.environ.setdefault('PIPEEDGE_QUEUE_DEPTH', '3')
     from pipeedge_b200 import ops
-    from pipeedge_b200.comm.p2p import DistP2pContext, DistP2pPipelineStage
+    from pipeedge_b200.comm.p2p import DistP2pContext, DistP2pPipelineStage, queue_depth
     import runtime as rt
     rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
     local = int(os.environ.get('LOCAL_RANK', rank))
@@ -486,6 +490,7 @@ def run_pipeline(args, spec, ubatch, seq, qbit, metric, unit, workload):
                     'dtype': 'f16', 'data': 'synthetic',
                     'config': {'workload': workload, 'model': spec.name, 'ubatch': ubatch, 'seq_len': seq_eff,
                                'partition': [list(p) for p in parts], 'quant': qbit, 'cuda_graph': True,
+                               'queue_depth': queue_depth(),
                                'hop': 'NCCL P2P per-direction communicators, fp32 activations'
                                       + (f' quantised to {qbit} bits' if qbit else ''),
                                'l2': f"timed loop rotates over {N_INPUTS} distinct resident micro-batches; per-stage "
@@ -509,6 +514,7 @@ def run_pipeline(args, spec, ubatch, seq, qbit, metric, unit, workload):
 
 
 def main():
+    faulthandler.enable()   # a native crash in any thread prints every thread's Python stack to stderr
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=300)
@@ -532,6 +538,12 @@ def main():
         raise SystemExit("bench.py: no CUDA device - pipeedge_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     if world > 1:
         run_pipeline(args, spec, ubatch, seq, qbit, metric, unit, args.workload)
+        # Every hop, thread and process group is shut down by now. Leave without the interpreter's and the CUDA / NCCL
+        # libraries' exit-time teardown: with 4 ranks one of them regularly died with SIGSEGV inside it (after
+        # Py_Finalize: faulthandler was already off), which torchrun reports as a failed job.
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     else:
         run_single_gpu(args, spec, ubatch, seq, qbit, metric, unit, args.workload)
 

@@ -399,12 +399,15 @@ class TensorSendThread(AbstractTensorExchangeThread):
         try:
             self._run(group)
         finally:
-            if self._hop is not None:
-                if self._inflight:
-                    self._inflight[-1].synchronize()
-                self._hop.close()
+            if self._hop is not None and self._inflight:
+                self._inflight[-1].synchronize()     # every send has left: the peer's matching receives complete too
             try:   # tell the receiver this hop is closing, so that its blocking receive returns
                 self._sock.sendall(_ENV_HEAD.pack(-1, 0))
+            except OSError:
+                pass
+            if self._hop is not None:
+                self._hop.close()                    # both ends now destroy the hop's communicator at about the same time
+            try:
                 self._sock.close()
             except OSError:
                 pass

@@ -12,6 +12,7 @@
 // itself carries no link-time NCCL dependency.
 // Replaces TensorSendThread.run / TensorRecvThread.run + _send_tensor / _recv_tensor (p2p/__init__.py:96-258).
 #include <dlfcn.h>
+#include <mutex>
 #include <errno.h>
 #include <string.h>
 #include <sys/socket.h>
@@ -63,6 +64,13 @@ static NcclApi& nccl() {
     }
   }
   return api;
+}
+
+// Communicator creation / destruction touch process-wide NCCL state (proxy service, shared resources): the send and
+// receive threads of a stage close their hops at about the same time, so those calls are serialised per process.
+static std::mutex& comm_lifecycle_mutex() {
+  static std::mutex m;
+  return m;
 }
 
 static int write_all(int fd, const void* buf, size_t n) {
@@ -135,7 +143,13 @@ int pe_hop_open(int fd, int is_sender, pe_hop** out) {
   hop->fd = fd;
   hop->is_sender = is_sender;
   hop->comm = nullptr;
-  const ncclResult_t r = api.CommInitRank(&hop->comm, 2, id, is_sender ? 0 : 1);
+  ncclResult_t r;
+  {
+    // hops are opened one at a time per process, in the same global order on every rank (p2p/__init__.py), so holding
+    // the lock across the blocking rendezvous cannot deadlock
+    std::lock_guard<std::mutex> lock(comm_lifecycle_mutex());
+    r = api.CommInitRank(&hop->comm, 2, id, is_sender ? 0 : 1);
+  }
   if (r != 0) {
     set_error("ncclCommInitRank failed: %s", api.GetErrorString(r));
     delete hop;
@@ -147,7 +161,10 @@ int pe_hop_open(int fd, int is_sender, pe_hop** out) {
 
 int pe_hop_close(pe_hop* hop) {
   if (hop == nullptr) return PE_OK;
-  if (hop->comm != nullptr) pe::nccl().CommDestroy(hop->comm);
+  if (hop->comm != nullptr) {
+    std::lock_guard<std::mutex> lock(pe::comm_lifecycle_mutex());
+    pe::nccl().CommDestroy(hop->comm);
+  }
   delete hop;
   return PE_OK;
 }

@@ -315,3 +315,10 @@ if __name__ == "__main__":
     console_hndlr.setLevel(logging.INFO)
     logging.getLogger().addHandler(console_hndlr)
     main()
+    if torch.cuda.is_available():
+        # everything is shut down; skip the CUDA / NCCL libraries' exit-time teardown, which can crash after a clean
+        # multi-rank run (see bench.py)
+        logging.shutdown()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
