@@ -221,7 +221,40 @@ def make_shard(spec, weights, layer_start, layer_end):
     return classes[spec.family](hf_config(spec), cfg, weights)
 
 
-def roofline_from_profile(shard, sample, spec, ubatch, seq, peaks) -> dict:
+def dominant_kernel_us(spec, ubatch, seq, dev) -> float:
+    """Average launch duration (us) of the dominant kernel - the FC1 GEMM with its GELU epilogue - as it runs inside a
+    step: back-to-back launches in a CUDA graph (as in the stage's graph), each on a different weight copy so that the
+    weights stream from HBM like in a forward (copies total > 126 MB L2), CUDA events on the launching stream."""
+    from pipeedge_b200 import _lib, ops
+    m, n, k = ubatch * seq, spec.inter, spec.hidden
+    copies = max(8, int(200e6 // (n * k * 2)) + 1)
+    gen = torch.Generator(device=dev).manual_seed(7)
+    a = (torch.randn(m, k, device=dev, generator=gen)).half()
+    ws = [(torch.randn(n, k, device=dev, generator=gen) * 0.02).half() for _ in range(copies)]
+    bias = torch.zeros(n, device=dev)
+    out = torch.empty(m, n, device=dev, dtype=torch.float16)
+    side = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(side):
+        for i in range(3):
+            ops.linear(a, ws[i], bias, _lib.PE_EPI_GELU_F16, out=out, static_w=True)
+        side.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            for w in ws:
+                ops.linear(a, w, bias, _lib.PE_EPI_GELU_F16, out=out, static_w=True)
+        for _ in range(3):
+            graph.replay()
+        reps = 10
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record(side)
+        for _ in range(reps):
+            graph.replay()
+        end.record(side)
+        side.synchronize()
+    return start.elapsed_time(end) * 1e3 / (reps * copies)
+
+
+def roofline_from_profile(shard, sample, spec, ubatch, seq, peaks, step_ms=None) -> dict:
     """Per-kernel CUDA-event times of live eager forwards -> roofline of the dominant kernel (FC1 GEMM)."""
     stage = shard.stage
     acc = {}
@@ -241,12 +274,26 @@ def roofline_from_profile(shard, sample, spec, ubatch, seq, peaks) -> dict:
         breakdown[kind] = entry
     total_ms = sum(sum(v) for v in acc.values()) / 3
     dom = 'gemm_fc1'
-    achieved = breakdown[dom]['tflops']
+    # The per-kernel times above are bracketed by events, which serialise the launches (no programmatic-dependent-launch
+    # overlap) and add event latency to every kernel: they are upper bounds, good for shares. The dominant kernel's
+    # launch duration proper is measured back to back in a graph, as it runs in the step.
+    dom_us = dominant_kernel_us(spec, ubatch, seq, sample.device)
+    achieved = flops[dom] / (dom_us * 1e-6) / 1e12
     peak = peaks['bf16_tflops_sustained']   # timed inside a long step
+    launches = breakdown[dom]['launches_per_forward']
+    traffic = None   # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'ncu_traffic.json')) as f:
+            traffic = json.load(f)['dram_bytes_per_launch']
+    except (OSError, KeyError, ValueError):
+        pass
     return {'bound': 'tensor', 'kernel': 'gemm_tcgen05_kernel<PE_EPI_GELU_F16> (FC1)', 'achieved': achieved,
-            'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
+            'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic,
             'peak_source': f"{peaks['source']} bf16_tflops_sustained (MEASURED_PEAKS.json)",
-            'flops_per_launch': flops[dom], 'share_of_step': sum(acc[dom]) / 3 / total_ms,
+            'flops_per_launch': flops[dom], 'avg_launch_us': dom_us,
+            'method': 'CUDA events around a graph of back-to-back launches on distinct weight copies (> L2)',
+            'share_of_step': (launches * dom_us * 1e-3 / step_ms) if step_ms else sum(acc[dom]) / 3 / total_ms,
+            'share_of_step_event_bracketed': sum(acc[dom]) / 3 / total_ms,
             'all_gemm_tflops': sum(flops[k] * breakdown[k]['launches_per_forward'] for k in flops if k in breakdown
                                    and k.startswith('gemm')) / (sum(sum(acc[k]) for k in acc if k.startswith('gemm'))
                                                                 / 3 * 1e-3) / 1e12,
@@ -325,11 +372,11 @@ def run_single_gpu(args, spec, ubatch, seq, qbit, metric, unit, workload):
     e2e = {'value': steps * ubatch / e2e_s, 'unit': unit, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
            'ms_per_step': e2e_s / steps * 1e3}
 
-    # ---- roofline of the dominant kernel, from per-kernel events inside live forwards
+    # ---- roofline of the dominant kernel (graph of back-to-back launches) + per-kernel shares (event-bracketed forwards)
     peaks = load_peaks()
     with torch.cuda.stream(stream):
         emb = shard.vit._embed(inputs_dev[0]) if spec.family != 'bert' else shard.bert._embed(inputs_dev[0])  # noqa
-        roof = roofline_from_profile(shard, emb, spec, ubatch, seq_eff, peaks)
+        roof = roofline_from_profile(shard, emb, spec, ubatch, seq_eff, peaks, step_ms=ms / steps)
     total_flops = flops_per_item(spec, seq_eff)
 
     out = {

@@ -45,6 +45,9 @@ extern "C" {
 #define PE_EPI_RESID_F32 2  /* out f32 = . + resid(f32)                  (ViTSelfOutput+skip, ViTOutput; BERT pre-LN sums) */
 #define PE_EPI_F32 3        /* out f32                                   (classifier heads)         */
 #define PE_EPI_TANH_F32 4   /* out f32 = tanh(.)                         (BertPooler)               */
+/* OR-able into `epilogue`: W is not written by any work still pending on `stream` (model weights). The kernel may then
+ * stream W into shared memory / L2 before its programmatic dependency on the preceding kernel resolves. */
+#define PE_EPI_STATIC_W 0x100
 
 int pe_abi_version(void);
 const char* pe_last_error(void);

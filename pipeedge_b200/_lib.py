@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_PKG_DIR, 'libpipeedge_b200.so')
 PE_OK = 0
 PE_FAMILY = {'vit': 0, 'deit': 1, 'bert': 2}
 PE_EPI_F16, PE_EPI_GELU_F16, PE_EPI_RESID_F32, PE_EPI_F32, PE_EPI_TANH_F32 = range(5)
+PE_EPI_STATIC_W = 0x100   # OR-able flag: W is a model weight (not produced by pending work on the stream)
 PE_CLAMP_NONE, PE_CLAMP_AUTO, PE_CLAMP_LAPLACE, PE_CLAMP_GELU = range(4)
 
 

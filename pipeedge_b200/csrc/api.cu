@@ -105,8 +105,8 @@ int pe_residual_layernorm(const void* y, const void* resid, const void* gamma, c
 
 int pe_linear(const void* a, const void* w, const void* bias, const void* resid, void* out, int m, int n, int k,
               int epilogue, void* stream) {
-  return pe::linear_impl(a, w, bias, resid, out, m, n, k, epilogue, 0, 0, 0, 0, /*static_w=*/0,
-                         static_cast<cudaStream_t>(stream));
+  return pe::linear_impl(a, w, bias, resid, out, m, n, k, epilogue & 0xff, 0, 0, 0, 0,
+                         /*static_w=*/(epilogue & PE_EPI_STATIC_W) != 0 ? 1 : 0, static_cast<cudaStream_t>(stream));
 }
 
 int pe_debug_linear_simt(const void* a, const void* w, const void* bias, const void* resid, void* out, int m, int n,

@@ -749,7 +749,7 @@ int linear_impl(const void* a, const void* w, const void* bias, const void* resi
   p.out_item_rows = out_item_rows;
   p.out_row_offset = out_row_offset;
   p.resid_per_item = resid_per_item;
-  p.static_w = (static_w != 0 || getenv("PE_GEMM_STATIC_W") != nullptr) ? 1 : 0;   // env: tuning scripts only
+  p.static_w = static_w != 0 ? 1 : 0;
 
   CUtensorMap ta, tb;   // each CTA loads its SLICE of a tile: 128/CN rows of A, BN/CM rows of W
   rc = encode_f16_2d(&ta, a, static_cast<uint64_t>(m), static_cast<uint64_t>(k), static_cast<uint32_t>(kBlockM / p.cn));

@@ -62,8 +62,9 @@ _EPI_OUT = {_lib.PE_EPI_F16: torch.float16, _lib.PE_EPI_GELU_F16: torch.float16,
 
 def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilogue: int,
            resid: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-           debug_simt: bool = False) -> torch.Tensor:
-    """`epilogue(a @ w.T + bias)`; a f16 [..., k], w f16 [n, k] (nn.Linear layout)."""
+           debug_simt: bool = False, static_w: bool = False) -> torch.Tensor:
+    """`epilogue(a @ w.T + bias)`; a f16 [..., k], w f16 [n, k] (nn.Linear layout). `static_w`: w is a model weight,
+    not written by work still pending on the stream (lets the kernel fetch it ahead of the preceding kernel's end)."""
     _want(a, torch.float16, 'a')
     _want(w, torch.float16, 'w')
     k = a.shape[-1]
@@ -80,7 +81,8 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilo
     else:
         _want(out, _EPI_OUT[epilogue], 'out')
     fn = LIB.pe_debug_linear_simt if debug_simt else LIB.pe_linear
-    check(fn(a.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(resid), out.data_ptr(), m, n, k, epilogue, _stream()))
+    flags = _lib.PE_EPI_STATIC_W if (static_w and not debug_simt) else 0
+    check(fn(a.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(resid), out.data_ptr(), m, n, k, epilogue | flags, _stream()))
     return out
 
 

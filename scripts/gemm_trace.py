@@ -23,13 +23,13 @@ for name, (m, n, k, epi) in SHAPES.items():
         os.environ['PE_GEMM_FORCE'] = plan
         os.environ['PE_GEMM_DEBUG_MODE'] = mode
         for _ in range(2):
-            ops.linear(a, w, bias, epi, resid=resid)
+            ops.linear(a, w, bias, epi, resid=resid, static_w=True)
         torch.cuda.synchronize()
         trace.zero_()
         LIB.pe_debug_gemm_trace(trace.data_ptr())
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        ops.linear(a, w, bias, epi, resid=resid)
+        ops.linear(a, w, bias, epi, resid=resid, static_w=True)
         e.record()
         torch.cuda.synchronize()
         LIB.pe_debug_gemm_trace(None)

@@ -20,12 +20,12 @@ for name, (m, n, k, epi) in SHAPES.items():
         side = torch.cuda.Stream()
         with torch.cuda.stream(side):
             for i in range(3):
-                ops.linear(a, ws[i], bias, epi, out=out)
+                ops.linear(a, ws[i], bias, epi, out=out, static_w=True)
             side.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=side):
                 for i in range(N):
-                    ops.linear(a, ws[i if mode == 'cold' else 0], bias, epi, out=out)
+                    ops.linear(a, ws[i if mode == 'cold' else 0], bias, epi, out=out, static_w=True)
         torch.cuda.synchronize()
         for _ in range(3):
             g.replay()

@@ -27,12 +27,12 @@ for name in only:
         side = torch.cuda.Stream()
         with torch.cuda.stream(side):
             for i in range(3):
-                ops.linear(a, ws[i], bias, epi, out=out)
+                ops.linear(a, ws[i], bias, epi, out=out, static_w=True)
             side.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=side):
                 for i in range(N):
-                    ops.linear(a, ws[i], bias, epi, out=out)
+                    ops.linear(a, ws[i], bias, epi, out=out, static_w=True)
         torch.cuda.synchronize()
         for _ in range(3):
             g.replay()

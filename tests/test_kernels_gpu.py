@@ -121,6 +121,21 @@ def test_linear_resid_in_place(ops):
     torch.testing.assert_close(buf.cpu(), want, rtol=5e-5, atol=5e-5)
 
 
+def test_linear_static_weight_flag(ops):
+    """PE_EPI_STATIC_W (weights fetched ahead of the programmatic dependency) changes timing, not results; back-to-back
+    launches exercise the overlap with a predecessor that is still running."""
+    lib = _lib()
+    a, w, bias, resid = _gemm_case(1576, 3072, 768, 21)
+    want = _gemm_ref(a, w, bias, resid, lib.PE_EPI_GELU_F16)
+    ad, wd, bd = a.cuda(), w.cuda(), bias.cuda()
+    torch.cuda.synchronize()
+    outs = [ops.linear(ad, wd, bd, lib.PE_EPI_GELU_F16, static_w=True) for _ in range(4)]
+    plain = ops.linear(ad, wd, bd, lib.PE_EPI_GELU_F16)
+    for o in outs:
+        assert torch.equal(o, plain)
+    torch.testing.assert_close(plain.cpu().float(), want, rtol=2e-3, atol=2e-3)
+
+
 def test_linear_rejects_bad_arguments(ops):
     lib = _lib()
     a, w, bias, _ = _gemm_case(16, 16, 12, 1)     # k % 8 != 0
