@@ -14,6 +14,9 @@ Fixture contents
 * `quant.npz`: `tensor_encode_outerdim` outputs and `tensor_decode_outerdim` round trips for
   several bit widths, plus the two runtime hooks' clamp thresholds (restated in this script
   without the `monitoring` calls - `runtime.py` itself cannot be imported here).
+* `adaptive.json` (`python -m oracle.make_goldens adaptive`): outputs of the reference's adaptive-QuantPipe policy
+  code (`/root/reference/utils/{quant,controller}.py`): `constrain_max_bitwidth` over a grid, Kalman-filter and
+  bit-width-controller traces for fixed measurement sequences.
 """
 import os
 import sys
@@ -130,9 +133,77 @@ def golden_quant():
     print('quant done')
 
 
+def _ref_utils():
+    """The reference's top-level `utils` package, imported under another name (this repo has its own `utils`)."""
+    import importlib.util   # pylint: disable=import-outside-toplevel
+    sys.path.insert(0, REF_SRC)   # `utils/quant.py` imports pipeedge.quantization.basic_op
+    pkg_dir = '/root/reference/utils'
+    spec = importlib.util.spec_from_file_location('ref_utils', os.path.join(pkg_dir, '__init__.py'),
+                                                  submodule_search_locations=[pkg_dir])
+    pkg = importlib.util.module_from_spec(spec)
+    sys.modules['ref_utils'] = pkg
+    spec.loader.exec_module(pkg)
+    import ref_utils.controller as ref_controller   # pylint: disable=import-outside-toplevel,import-error
+    import ref_utils.quant as ref_quant             # pylint: disable=import-outside-toplevel,import-error
+    return ref_quant, ref_controller
+
+
+def golden_adaptive():
+    """Adaptive QuantPipe policy code of the reference on fixed inputs -> tests/golden/adaptive.json."""
+    import json   # pylint: disable=import-outside-toplevel
+    ref_quant, ref_controller = _ref_utils()
+    out = {}
+    grid = []
+    for t_max in (0.0, 0.001, 0.004, 0.01, 0.05, 1.0, float('inf')):
+        for d_size in (0.0, 4.84, 38.7, 154.9):            # Mbits of a payload
+            for d_speed in (0.0, 10.0, 1000.0, 25000.0):   # Mbit/s
+                for bw_max in (32, 16):
+                    try:
+                        got = int(ref_quant.constrain_max_bitwidth(torch.tensor(t_max), torch.tensor(d_size),
+                                                                   torch.tensor(d_speed), torch.tensor(bw_max)))
+                    except IndexError:   # 0/0 or inf*0: NaN compares false everywhere, the reference indexes []
+                        got = -1
+                    grid.append([t_max, d_size, d_speed, bw_max, got])
+    out['constrain_max_bitwidth'] = grid
+    rng = np.random.default_rng(5)
+    kalman = []
+    for x0, p0 in ((0.0, 1.0), (3.0, 0.5)):
+        filt = ref_controller.KalmanFilter(x_hat_0=x0, p_0=p0)
+        zs = (10.0 + rng.normal(0, 0.5, 20)).tolist()
+        hs = (1.0 + rng.uniform(0, 2, 20)).tolist()
+        kalman.append({'x0': x0, 'p0': p0, 'z': zs, 'h': hs, 'x_hat': [float(filt(z, h)) for z, h in zip(zs, hs)]})
+    out['kalman'] = kalman
+    xup = []
+    for ref_value, u0, umax, pole in ((100.0, 1.0, 16.0, 0.0), (40.0, 2.0, 8.0, 0.5), (7.5, 1.0, float('inf'), 0.9)):
+        ctl = ref_controller.AdaptiveIntegralXupController(ref_value, u0, u_max=umax, pole=pole)
+        ys = (ref_value * rng.uniform(0.3, 1.6, 25)).tolist()
+        xup.append({'reference': ref_value, 'u_0': u0, 'u_max': umax, 'pole': pole, 'y': ys,
+                    'u': [float(ctl(y)) for y in ys]})
+    out['xup'] = xup
+    basic_op = _ref()[2]
+    bitwidths = [i for i in range(32, 1, -1)
+                 if int(basic_op.compression_factor(i)) > int(basic_op.compression_factor(i + 1))]
+    out['bitwidths'] = bitwidths
+    traces = []
+    for constraint, start, window in ((100.0, 32, 10), (2500.0, 8, 10), (30.0, 2, 7), (0.0, 32, 10)):
+        ctl = ref_quant.AdaptiveBitwidthPerformanceController(0, bitwidths, start)
+        ctl.reference = constraint
+        perf = (max(constraint, 10.0) * rng.uniform(0.2, 2.0, 30)).tolist()
+        traces.append({'constraint': constraint, 'start': start, 'window': window, 'perf': perf,
+                       'out': [list(map(int, ctl(p, window))) for p in perf]})
+    out['bitwidth_controller'] = traces
+    with open(os.path.join(OUT, 'adaptive.json'), 'w', encoding='utf8') as f:
+        json.dump(out, f)
+    print('adaptive done')
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if sys.argv[1:] == ['adaptive']:
+        golden_adaptive()
+        return
+    golden_adaptive()
     golden_quant()
     for name in ('test/vit-tiny', 'test/deit-tiny', 'test/bert-tiny'):
         golden_tiny(name)

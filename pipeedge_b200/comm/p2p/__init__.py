@@ -21,6 +21,7 @@ for one rank per B200:
 Without CUDA (the CPU test-suite) everything rides Gloo and the classes behave like the reference's.
 """
 import collections
+import logging
 import os
 import pickle
 import queue
@@ -33,6 +34,8 @@ import ctypes
 import torch
 import torch.distributed as dist
 from .. import DistCmdHandler, DistContext
+
+logger = logging.getLogger(__name__)
 
 # Gloo message tags
 TAG_CMD = 10          # [cmd, n_tensors, sender rank]
@@ -383,6 +386,22 @@ class TensorSendThread(AbstractTensorExchangeThread):
         self._sock = None
         self._hop = None
         self._inflight = collections.deque()
+        self._timing_hooks: List[Tuple[Callable[..., None], tuple]] = []
+        self._timed = collections.deque()     # (start event, done event, Mbits) of sends not yet reported
+
+    def register_timing_hook(self, hook: Callable[..., None], args: tuple) -> None:
+        """`hook(mbits, seconds, *args)` is called on this thread once a payload's device-side transfer has finished:
+        `seconds` is the time between the CUDA events around its NCCL sends on the hop stream (it includes waiting
+        for the receiver to post its buffers, like the reference's blocking send), `mbits` the bytes moved * 8e-6."""
+        self._timing_hooks.append((hook, args))
+
+    def _report_timed(self, drain: bool = False) -> None:
+        while self._timed and (drain or self._timed[0][1].query()):
+            start, done, mbits = self._timed.popleft()
+            done.synchronize()
+            seconds = start.elapsed_time(done) * 1e-3
+            for hook, args in self._timing_hooks:
+                hook(mbits, seconds, *args)
 
     def stop(self) -> None:
         """Direct the thread to stop."""
@@ -401,6 +420,10 @@ class TensorSendThread(AbstractTensorExchangeThread):
         finally:
             if self._hop is not None and self._inflight:
                 self._inflight[-1].synchronize()     # every send has left: the peer's matching receives complete too
+            try:
+                self._report_timed(drain=True)
+            except Exception:   # pylint: disable=broad-except
+                logger.exception("hop timing hook failed during shutdown")
             try:   # tell the receiver this hop is closing, so that its blocking receive returns
                 self._sock.sendall(_ENV_HEAD.pack(-1, 0))
             except OSError:
@@ -460,8 +483,20 @@ class TensorSendThread(AbstractTensorExchangeThread):
                 # native fast path: envelope header + NCCL sends + event record in one GIL-free call
                 for tensor in cuda:
                     tensor.record_stream(self._stream)
-                done = _fresh_event(self._stream)
-                hop.send(cuda, payload.ready, self._stream, done, write_envelope=fast)
+                if self._timing_hooks:
+                    # device-side hop time: events on the hop stream right before / after the sends
+                    self._report_timed()
+                    if payload.ready is not None:
+                        self._stream.wait_event(payload.ready)
+                    start = torch.cuda.Event(enable_timing=True)
+                    start.record(self._stream)
+                    done = torch.cuda.Event(enable_timing=True)
+                    done.record(self._stream)   # creates the handle; re-recorded by the hop after the sends
+                    hop.send(cuda, None, self._stream, done, write_envelope=fast)
+                    self._timed.append((start, done, sum(t.numel() * t.element_size() for t in cuda) * 8e-6))
+                else:
+                    done = _fresh_event(self._stream)
+                    hop.send(cuda, payload.ready, self._stream, done, write_envelope=fast)
                 if payload.on_consumed is not None:
                     payload.on_consumed(done)
                 self._inflight.append(done)
@@ -827,6 +862,15 @@ class DistP2pPipelineStage:
         thr = self._threads.get('send')
         if thr is not None:
             thr.register_post_hook(hook, args)
+
+    def register_send_timing_hook(self, hook: Callable[..., None], args: tuple) -> None:
+        """Register `hook(mbits, seconds, *args)`, called with each payload's DEVICE-side transfer time (CUDA events
+        around the hop's NCCL sends). The send post hook above fires when a send is enqueued, not when it has
+        finished, so bandwidth-driven policies (`runtime.py:121-216` in the reference) read this instead. No
+        reference equivalent: there the blocking send itself is timed on the host."""
+        thr = self._threads.get('send')
+        if thr is not None:
+            thr.register_timing_hook(hook, args)
 
     def __enter__(self):
         self.init()

@@ -5,9 +5,11 @@ Same CLI (`runtime.py:610-687`): `runtime.py RANK WORLDSIZE [-d] [-s] [--addr] [
 stage output, `-r` stage-to-rank order, `-D` data rank), same command protocol (CMD_STOP / CMD_SCHED) and the
 same hook structure around the shard (`run_pipeline_p2p`, `runtime.py:418-511`). One rank per B200:
 activations stay in HBM, the hop is NCCL on a side stream, and the QuantPipe hooks call the fused device
-kernels (bit-identical codes). What is NOT carried over (out of scope): the RPC
-backend (`-c rpc`), `sched-pipeline` automated scheduling (`-H/-sm/-sdt/-sd`), monitoring heartbeats, and the
-dataset loaders that need the network; inputs are the reference's synthetic fallback (`runtime.py:386-400`)
+kernels (bit-identical codes). The adaptive QuantPipe policies (`ADAPTIVE_QUANT=HEURISTIC|HEURISTIC2|CONTROLLER`
+with `SEND_CONSTRAINT` items/s and `WINDOW_SIZE`, `runtime.py:121-216`) are carried over; they read the hop's
+DEVICE-side transfer time (CUDA events around the NCCL sends) through `monitoring.py`'s window statistics.
+What is NOT carried over (out of scope): the RPC backend (`-c rpc`), `sched-pipeline`
+automated scheduling (`-H/-sm/-sdt/-sd`), energy monitoring, and the dataset loaders that need the network; inputs are the reference's synthetic fallback (`runtime.py:386-400`)
 generated locally, weights come from `-M` (an npz in the reference layout) or are synthesised.
 """
 import argparse
@@ -23,17 +25,41 @@ import torch
 from torch.utils.data import DataLoader, Dataset
 from pipeedge_b200 import models
 from pipeedge_b200.comm.p2p import DistP2pContext
-from pipeedge_b200.quantization.basic_op import tensor_decode_outerdim, tensor_encode_outerdim
+from pipeedge_b200.quantization.basic_op import compression_factor, tensor_decode_outerdim, tensor_encode_outerdim
 from pipeedge_b200.synth import MODEL_SPECS, synth_input, synth_weights
 import devices
 import model_cfg
+import monitoring
+from utils import quant as quantutil
 
 logger = logging.getLogger(__name__)
 
 CMD_STOP = 0
 CMD_SCHED = 1
 
+# A window period defines monitoring and configurability work intervals (`runtime.py:39-44`)
+WINDOW_SIZE = 10
+ENV_WINDOW_SIZE: str = "WINDOW_SIZE"
+
+
+def get_window_size() -> int:
+    """Get the window size."""
+    return int(os.getenv(ENV_WINDOW_SIZE, str(WINDOW_SIZE)))
+
+
 ENV_SEND_CONSTRAINT: str = "SEND_CONSTRAINT"
+
+ENV_ADAPTIVE_QUANT: str = "ADAPTIVE_QUANT"
+ADAPTIVE_QUANT_HEURISTIC = "HEURISTIC"
+ADAPTIVE_QUANT_HEURISTIC2 = "HEURISTIC2"
+ADAPTIVE_QUANT_CONTROLLER = "CONTROLLER"
+
+MONITORING_KEY_MODEL = 'shard'
+MONITORING_KEY_OUTPUT = 'output'
+MONITORING_KEY_QUANT_DECODE = 'quant_decode'
+MONITORING_KEY_QUANT_ENCODE = 'quant_encode'
+MONITORING_KEY_RECV = 'recv'
+MONITORING_KEY_SEND = 'send'
 
 
 def forward_hook_quant_encode(module, _input_arg, output: Union[torch.Tensor, Tuple[torch.Tensor, ...]]):
@@ -63,6 +89,102 @@ def forward_pre_hook_quant_decode(_module, input_arg: Tuple[Tuple[torch.Tensor, 
     if len(forward_tensor) == 1:
         return tuple(forward_tensor)        # a single tensor payload
     return (tuple(forward_tensor),)         # a (data, skip) tuple payload
+
+
+def _payload_tensors(outputs) -> Tuple[torch.Tensor, ...]:
+    return (outputs,) if isinstance(outputs, torch.Tensor) else tuple(outputs)
+
+
+def _send_window(*getters: str):
+    """Consistent read of the send key's tag, window size and the requested `get_window_*` values."""
+    with monitoring.get_locked_context(MONITORING_KEY_SEND) as mctx:
+        tag = mctx.get_tag(key=MONITORING_KEY_SEND)
+        window_size = mctx.get_window_size(key=MONITORING_KEY_SEND)
+        values = tuple(getattr(mctx, 'get_window_' + g)(key=MONITORING_KEY_SEND) for g in getters)
+    return (tag, window_size) + values
+
+
+def forward_hook_set_quant_bandwidth_heuristic(module, _inputs, outputs) -> None:
+    """Pick the quantization bit-width whose compression fits the window's send budget (`runtime.py:121-154`).
+
+    Every `window_size` sends: budget = time the rate constraint allows for one window x measured hop bandwidth
+    (Mbit/s); needed compression = what the window actually sent, scaled back to 32-bit, over that budget; mapped to
+    32/16/8/6/4/2 bits by fixed thresholds."""
+    tag, window_size, bandwidth, sent_mbits = _send_window('perf', 'work')
+    if tag == 0 or tag % window_size != 0:
+        return
+    target_rate = module.rate_constraint.item()
+    if target_rate > 0:
+        ubatch_size = models.get_microbatch_size(outputs, verify=True)
+        budget_mbits = ubatch_size * window_size / target_rate * bandwidth
+    else:
+        budget_mbits = float('inf')
+    quant_bit = module.quant_bit.item()
+    unquantized_mbits = sent_mbits * (32 / quant_bit) if quant_bit > 0 else sent_mbits
+    compress_ratio = int(unquantized_mbits / budget_mbits) + 1
+    for limit, bits in ((1, 0), (2, 16), (4, 8), (5, 6), (8, 4)):
+        if compress_ratio <= limit:
+            module.quant_bit = torch.tensor(bits)
+            break
+    else:
+        module.quant_bit = torch.tensor(2)
+    logger.info("Adaptive quantization (heuristic): bitwidth=%d", int(module.quant_bit))
+
+
+def forward_hook_set_quant_bandwidth_heuristic_2(module, _inputs, outputs) -> None:
+    """Largest bit-width that moves one micro-batch within its share of the rate constraint (`runtime.py:156-177`)."""
+    tag, window_size, bandwidth = _send_window('perf')
+    if tag == 0 or tag % window_size != 0:
+        return
+    tensors = _payload_tensors(outputs)
+    ubatch_size = models.get_microbatch_size(outputs, verify=True)
+    ubatch_time = ubatch_size / module.rate_constraint            # rate 0 -> inf: anything fits
+    ubatch_mbits = sum(t.numel() * t.element_size() for t in tensors) * 8 / 1000000
+    src_bit = torch.tensor(tensors[0].element_size() * 8)
+    quant_bit = quantutil.constrain_max_bitwidth(ubatch_time, ubatch_mbits, bandwidth, src_bit)
+    # at least 2 bits; the source width itself means "do not quantize" (0)
+    module.quant_bit = max(torch.tensor(2), quant_bit) % src_bit
+    logger.info("Adaptive quantization (heuristic2): bitwidth=%d", int(module.quant_bit))
+
+
+# Largest bitwidths in range [2, 32] with unique discrete compressions (`runtime.py:179-181`)
+BITWIDTHS = [i for i in range(32, 1, -1)
+             if int(compression_factor(i)) > int(compression_factor(i + 1))]
+# controllers are host objects and cannot live in a Module's buffers: cached per module
+_MODULE_QUANT_CONTROLLERS = {}
+_MODULE_QUANT_CONTROLLERS_LOCK = threading.Lock()
+
+
+def forward_hook_set_quant_controller(module, _inputs, outputs) -> None:
+    """Feedback controller: split each window between two adjacent bit-widths so that the measured send rate
+    (items/s) tracks `rate_constraint` (`runtime.py:182-215`). The plan lives in the module's `bitwidth1`,
+    `bitwidth2`, `bitwidth1_iters` buffers; `quant_bit` is set for the micro-batch about to be sent."""
+    bw1 = int(module.bitwidth1.item()) if hasattr(module, 'bitwidth1') else 0
+    bw2 = int(module.bitwidth2.item()) if hasattr(module, 'bitwidth2') else 0
+    bw1_iters = int(module.bitwidth1_iters.item()) if hasattr(module, 'bitwidth1_iters') else 0
+    tag, window_size, heartrate = _send_window('heartrate')
+    if tag > 0 and tag % window_size == 0:
+        with _MODULE_QUANT_CONTROLLERS_LOCK:
+            bw_ctlr = _MODULE_QUANT_CONTROLLERS.get(module)
+            if bw_ctlr is None:
+                bw_start = module.quant_bit.item() or max(BITWIDTHS)        # not quantizing = the widest setting
+                bw_ctlr = quantutil.AdaptiveBitwidthPerformanceController(0, BITWIDTHS, bw_start)
+                _MODULE_QUANT_CONTROLLERS[module] = bw_ctlr
+        bw_ctlr.reference = module.rate_constraint.item()
+        send_rate = heartrate * models.get_microbatch_size(outputs, verify=True)
+        bw1, bw2, bw1_iters = bw_ctlr(send_rate, window_size)
+        module.register_buffer('bitwidth1', torch.tensor(bw1), persistent=False)
+        module.register_buffer('bitwidth2', torch.tensor(bw2), persistent=False)
+        logger.info("Adaptive quantization (controller): bitwidth1=%d (iters=%d), bitwidth2=%d", bw1, bw1_iters, bw2)
+    bitwidth = bw1 if bw1_iters > 0 else bw2
+    module.quant_bit = torch.tensor(bitwidth % max(BITWIDTHS))               # the widest setting = no quantization
+    module.register_buffer('bitwidth1_iters', torch.tensor(max(0, bw1_iters - 1)), persistent=False)
+
+
+def hop_timing_hook_monitor(mbits: float, seconds: float, key: str) -> None:
+    """One completed hop transfer -> one heartbeat of `key` with the device-measured duration (replaces the
+    reference's host-timed `p2p_pre_hook_monitor` / `p2p_post_hook_monitor` pair, `runtime.py:218-230`)."""
+    monitoring.iteration(key, work=mbits, seconds=seconds)
 
 
 class ThreadSafeCounter:
@@ -184,6 +306,7 @@ def run_pipeline_p2p(world_size: int, rank: int, model_name: str, model_file: Op
                      rank_order: Optional[List[int]], data_rank: int) -> float:
     """Run the pipeline using P2P communication (`runtime.py:418-511`); returns throughput on the data rank."""
     throughput = 0.0
+    monitoring.init(MONITORING_KEY_SEND, get_window_size(), work_type='Mbits')
     with DistP2pContext(('gloo',), {'world_size': world_size, 'rank': rank}, handle_cmd) as dist_ctx:
         if rank == 0:
             stage_layers, stage_quant, stage_ranks = get_pipeline_sched(world_size, partition, quant, rank_order,
@@ -215,12 +338,21 @@ def run_pipeline_p2p(world_size: int, rank: int, model_name: str, model_file: Op
             model.register_buffer('rate_constraint', torch.tensor(send_constraint), persistent=False)
             model.register_forward_hook(devices.forward_hook_to_cpu)
             if stage != len(stage_ranks) - 1:
+                quant_impl = os.getenv(ENV_ADAPTIVE_QUANT)
+                if quant_impl == ADAPTIVE_QUANT_CONTROLLER:
+                    model.register_forward_hook(forward_hook_set_quant_controller)
+                elif quant_impl == ADAPTIVE_QUANT_HEURISTIC:
+                    model.register_forward_hook(forward_hook_set_quant_bandwidth_heuristic)
+                elif quant_impl == ADAPTIVE_QUANT_HEURISTIC2:
+                    model.register_forward_hook(forward_hook_set_quant_bandwidth_heuristic_2)
                 model.register_forward_hook(forward_hook_quant_encode)
             if stage != 0:
                 model.register_forward_pre_hook(forward_pre_hook_quant_decode)
             model.register_forward_pre_hook(devices.forward_pre_hook_to_device)
         with model_cfg.dist_p2p_pipeline_stage_factory(stage_ranks, data_rank, rank, stage, model,
                                                        handle_results) as stage_ctx:
+            if os.getenv(ENV_ADAPTIVE_QUANT):
+                stage_ctx.register_send_timing_hook(hop_timing_hook_monitor, (MONITORING_KEY_SEND,))
             if rank == data_rank:
                 dataset = load_dataset(model_name, batch_size, ubatch_size)
                 data_loader = DataLoader(dataset, batch_size=ubatch_size)
@@ -238,6 +370,7 @@ def run_pipeline_p2p(world_size: int, rank: int, model_name: str, model_file: Op
                 stop_event.set()
             else:
                 stop_event.wait()
+    monitoring.finish()
     return throughput
 
 

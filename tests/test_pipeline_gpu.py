@@ -131,3 +131,40 @@ def test_two_stage_pipeline_over_nccl(name, cuts, qbits):
             x = synth_input(spec, ubatch, seed=10 + i, seq_len=32)
             want = osh.shard_forward(spec, w, 1, spec.layers, x).numpy()
             assert np.abs(logits - want).max() <= 4e-3 * np.abs(want).max(), f"ubatch {i}"
+
+
+@pytest.mark.parametrize('policy', ['HEURISTIC', 'HEURISTIC2', 'CONTROLLER'])
+def test_runtime_cli_adaptive_quant(policy, tmp_path):
+    """`runtime.py` on 2 ranks with an adaptive QuantPipe policy and a send-rate constraint no hop can meet: the policy
+    reads the hop's device-side transfer times and must move the stage's bit-width off 'no quantization', and the run
+    must still deliver every result (`runtime.py:121-216,465-477` of the reference)."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import subprocess
+    import sys
+    port = _free_port()
+    env = dict(os.environ, ADAPTIVE_QUANT=policy, SEND_CONSTRAINT='1e9', WINDOW_SIZE='2', PYTHONUNBUFFERED='1')
+    cmd = [sys.executable, os.path.join(ROOT, 'runtime.py'), None, '2', '--port', str(port), '-m',
+           'facebook/deit-tiny-distilled-patch16-224', '-b', '64', '-u', '8', '-pt', '1,24,25,48', '-q', '0,0']
+    procs = []
+    for rank in (1, 0):
+        argv = list(cmd)
+        argv[2] = str(rank)
+        procs.append(subprocess.Popen(argv, cwd=str(tmp_path), env=dict(env, LOCAL_RANK=str(rank)), stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = []
+    for p in procs:
+        try:
+            out, _ = p.communicate(timeout=600)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            out, _ = p.communicate()
+        outs.append(out)
+    for p, out in zip(procs, outs):
+        assert p.returncode == 0, out[-3000:]
+    rank0 = outs[1]
+    assert 'throughput is' in rank0, rank0[-3000:]
+    import re
+    bits = [int(b) for b in re.findall(r'Adaptive quantization \(\w+\): bitwidth1?=(\d+)', rank0)]
+    assert bits, rank0[-3000:]
+    assert any(0 < b < 32 for b in bits), bits
