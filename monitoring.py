@@ -213,3 +213,52 @@ def iteration(key: str, work: Union[int, float] = 1, accuracy: Union[int, float]
             logger.debug("%s: Window Time: %s sec, Rate: %s /sec, Work: %s %s, Perf: %s %s/sec", key,
                          _ctx.get_window_time_s(key=key), _ctx.get_window_heartrate(key=key),
                          _ctx.get_window_work(key=key), _work_types[key], _ctx.get_window_perf(key=key), _work_types[key])
+
+
+class DeviceIterations:
+    """Iterations whose duration is measured ON THE DEVICE: `start(key)` / `finish(key, work, accuracy)` record CUDA
+    events on the current stream around work that was only enqueued; the pair is turned into a heartbeat
+    (`iteration(key, ..., seconds=elapsed)`) once the device has passed both, at a later `start`/`finish`/`harvest`
+    call - nothing here synchronises the stream. `event_factory` is injectable for tests."""
+
+    def __init__(self, event_factory=None):
+        if event_factory is None:
+            import torch   # pylint: disable=import-outside-toplevel
+
+            def event_factory():
+                evt = torch.cuda.Event(enable_timing=True)
+                evt.record()
+                return evt
+        self._event = event_factory
+        self._open = {}                        # (thread ident, key) -> start event
+        self._pending = collections.deque()    # (key, start, end, work, accuracy), in completion order per stream
+        self._lock = threading.Lock()
+
+    def start(self, key: str) -> None:
+        """Mark the start of an iteration of `key` on this thread's current stream."""
+        self.harvest()
+        self._open[(threading.get_ident(), key)] = self._event()
+
+    def finish(self, key: str, work: Union[int, float] = 1, accuracy: Union[int, float] = 0) -> None:
+        """Mark the end of the iteration started by `start(key)` on this thread."""
+        began = self._open.pop((threading.get_ident(), key), None)
+        if began is None:
+            raise KeyError(f"No device iteration in flight for key: {key}")
+        with self._lock:
+            self._pending.append((key, began, self._event(), work, accuracy))
+        self.harvest()
+
+    def harvest(self, drain: bool = False) -> int:
+        """Report every finished pair (all of them, waiting if necessary, with `drain`); returns how many."""
+        done = []
+        with self._lock:
+            while self._pending:
+                key, began, ended, work, accuracy = self._pending[0]
+                if not drain and not ended.query():
+                    break
+                self._pending.popleft()
+                done.append((key, began, ended, work, accuracy))
+        for key, began, ended, work, accuracy in done:
+            ended.synchronize()
+            iteration(key, work=work, accuracy=accuracy, seconds=began.elapsed_time(ended) * 1e-3)
+        return len(done)

@@ -61,6 +61,32 @@ MONITORING_KEY_QUANT_ENCODE = 'quant_encode'
 MONITORING_KEY_RECV = 'recv'
 MONITORING_KEY_SEND = 'send'
 
+# Per-kernel-group heartbeats ('shard', 'quant_encode', 'quant_decode', 'output') cost four CUDA event records per
+# micro-batch and stage, so unlike the reference they are opt-in: MONITORING=1. The 'send' key is always fed when an
+# adaptive quantization policy is active.
+ENV_MONITORING: str = "MONITORING"
+_device_iters = None   # monitoring.DeviceIterations when MONITORING=1
+
+
+def monitoring_enabled() -> bool:
+    """Whether the opt-in heartbeats are on."""
+    return _device_iters is not None
+
+
+def forward_pre_hook_monitor(_module, _inputs) -> None:
+    """Register iteration start (`runtime.py:60-62`): a CUDA event on the shard's stream."""
+    if _device_iters is not None:
+        _device_iters.start(MONITORING_KEY_MODEL)
+
+
+def forward_hook_monitor(module, _inputs, outputs) -> None:
+    """Register iteration completion (`runtime.py:64-71`): work = micro-batch size, accuracy = layers processed; the
+    duration is the device time between the two events."""
+    if _device_iters is not None:
+        n_items = models.get_microbatch_size(outputs, verify=True)
+        n_layers = module.shard_config.layer_end - module.shard_config.layer_start + 1
+        _device_iters.finish(MONITORING_KEY_MODEL, work=n_items, accuracy=n_layers)
+
 
 def forward_hook_quant_encode(module, _input_arg, output: Union[torch.Tensor, Tuple[torch.Tensor, ...]]):
     """Encode tensors in the forward hook, after the shard (`runtime.py:73-91`).
@@ -72,10 +98,16 @@ def forward_hook_quant_encode(module, _input_arg, output: Union[torch.Tensor, Tu
         output = (output,)
     assert isinstance(output, tuple)
     quant_bit = int(module.quant_bit.item())
+    if _device_iters is not None:
+        _device_iters.start(MONITORING_KEY_QUANT_ENCODE)
     comm_tuple = []
     for tensor in output:
         assert isinstance(tensor, torch.Tensor)
         comm_tuple += tensor_encode_outerdim(tensor, quant_bit, clamp=quant_bit > 0)
+    if _device_iters is not None:
+        # work = micro-batch size, but quantization only does work if quant_bit > 0 (`runtime.py:88-90`)
+        n_items = models.get_microbatch_size(output[0], verify=True) if quant_bit > 0 else 0
+        _device_iters.finish(MONITORING_KEY_QUANT_ENCODE, work=n_items, accuracy=quant_bit)
     return tuple(comm_tuple)
 
 
@@ -85,7 +117,13 @@ def forward_pre_hook_quant_decode(_module, input_arg: Tuple[Tuple[torch.Tensor, 
     input_tensors = input_arg[0]
     assert isinstance(input_tensors, tuple)
     assert len(input_tensors) % 5 == 0 and len(input_tensors) >= 5
+    if _device_iters is not None:
+        _device_iters.start(MONITORING_KEY_QUANT_DECODE)
     forward_tensor = [tensor_decode_outerdim(input_tensors[i * 5:i * 5 + 5]) for i in range(len(input_tensors) // 5)]
+    if _device_iters is not None:
+        quant_bit = int(input_tensors[4][0].item())     # same bit-width for all items (`runtime.py:103`)
+        n_items = models.get_microbatch_size(forward_tensor[0], verify=True) if quant_bit > 0 else 0
+        _device_iters.finish(MONITORING_KEY_QUANT_DECODE, work=n_items, accuracy=quant_bit)
     if len(forward_tensor) == 1:
         return tuple(forward_tensor)        # a single tensor payload
     return (tuple(forward_tensor),)         # a (data, skip) tuple payload
@@ -241,6 +279,11 @@ def handle_results(tensors: torch.Tensor) -> None:
         pred = tensors.argmax(dim=1).cpu()
         acc = pred.eq(ubatch_labels).sum().item()
         logger.debug("micro-batch accuracy: %d/%d", acc, n_items)
+    else:
+        acc = 0
+    if _device_iters is not None:
+        # time BETWEEN results, not pipeline latency: a heartbeat series without an explicit start (`runtime.py:239-255`)
+        monitoring.iteration(MONITORING_KEY_OUTPUT, work=n_items, accuracy=acc, safe=False)
     results_counter.add(n_items)
 
 
@@ -305,8 +348,15 @@ def run_pipeline_p2p(world_size: int, rank: int, model_name: str, model_file: Op
                      ubatch_size: int, partition: Optional[List[Tuple[int, int]]], quant: Optional[List[int]],
                      rank_order: Optional[List[int]], data_rank: int) -> float:
     """Run the pipeline using P2P communication (`runtime.py:418-511`); returns throughput on the data rank."""
+    global _device_iters   # pylint: disable=global-statement
     throughput = 0.0
     monitoring.init(MONITORING_KEY_SEND, get_window_size(), work_type='Mbits')
+    if os.getenv(ENV_MONITORING, '0') == '1':
+        monitoring.add_key(MONITORING_KEY_MODEL, work_type='tensors', acc_type='layers')
+        monitoring.add_key(MONITORING_KEY_OUTPUT, work_type='classifications', acc_type='correct')
+        monitoring.add_key(MONITORING_KEY_QUANT_DECODE, work_type='tensors', acc_type='bits')
+        monitoring.add_key(MONITORING_KEY_QUANT_ENCODE, work_type='tensors', acc_type='bits')
+        _device_iters = monitoring.DeviceIterations()
     with DistP2pContext(('gloo',), {'world_size': world_size, 'rank': rank}, handle_cmd) as dist_ctx:
         if rank == 0:
             stage_layers, stage_quant, stage_ranks = get_pipeline_sched(world_size, partition, quant, rank_order,
@@ -337,6 +387,7 @@ def run_pipeline_p2p(world_size: int, rank: int, model_name: str, model_file: Op
             send_constraint = float(os.getenv(ENV_SEND_CONSTRAINT, str(0)))
             model.register_buffer('rate_constraint', torch.tensor(send_constraint), persistent=False)
             model.register_forward_hook(devices.forward_hook_to_cpu)
+            model.register_forward_hook(forward_hook_monitor)
             if stage != len(stage_ranks) - 1:
                 quant_impl = os.getenv(ENV_ADAPTIVE_QUANT)
                 if quant_impl == ADAPTIVE_QUANT_CONTROLLER:
@@ -348,10 +399,11 @@ def run_pipeline_p2p(world_size: int, rank: int, model_name: str, model_file: Op
                 model.register_forward_hook(forward_hook_quant_encode)
             if stage != 0:
                 model.register_forward_pre_hook(forward_pre_hook_quant_decode)
+            model.register_forward_pre_hook(forward_pre_hook_monitor)
             model.register_forward_pre_hook(devices.forward_pre_hook_to_device)
         with model_cfg.dist_p2p_pipeline_stage_factory(stage_ranks, data_rank, rank, stage, model,
                                                        handle_results) as stage_ctx:
-            if os.getenv(ENV_ADAPTIVE_QUANT):
+            if os.getenv(ENV_ADAPTIVE_QUANT) or monitoring_enabled():
                 stage_ctx.register_send_timing_hook(hop_timing_hook_monitor, (MONITORING_KEY_SEND,))
             if rank == data_rank:
                 dataset = load_dataset(model_name, batch_size, ubatch_size)
@@ -370,6 +422,9 @@ def run_pipeline_p2p(world_size: int, rank: int, model_name: str, model_file: Op
                 stop_event.set()
             else:
                 stop_event.wait()
+    if _device_iters is not None:
+        _device_iters.harvest(drain=True)
+        _device_iters = None
     monitoring.finish()
     return throughput
 

@@ -157,3 +157,58 @@ def test_controller_hook(send_monitor):
             assert seen[-1] == want, (window, tag, plan)
             plan = (bw1, bw2, max(0, iters - 1))
     assert len(set(seen)) > 1                                   # the policy did move
+
+
+def test_device_iterations_with_fake_events():
+    """Device-timed heartbeats: pairs are reported only once the 'device' has passed the end event, in order, with the
+    elapsed time between the events; `harvest(drain=True)` waits for the rest."""
+    import monitoring
+
+    class FakeEvent:
+        clock = 0.0
+
+        def __init__(self):
+            self.t_ms = FakeEvent.clock
+            self.reached = False
+            self.waited = False
+
+        def query(self):
+            return self.reached
+
+        def synchronize(self):
+            self.waited = True
+            self.reached = True
+
+        def elapsed_time(self, other):
+            return other.t_ms - self.t_ms
+
+    created = []
+
+    def factory():
+        created.append(FakeEvent())
+        return created[-1]
+
+    monitoring.init('shard', 4, work_type='tensors', acc_type='layers')
+    try:
+        iters = monitoring.DeviceIterations(event_factory=factory)
+        for i in range(3):
+            FakeEvent.clock = 10.0 * i
+            iters.start('shard')
+            FakeEvent.clock = 10.0 * i + 2.0 + i          # 2, 3, 4 ms of "device" work
+            iters.finish('shard', work=8, accuracy=24)
+        with monitoring.get_locked_context('shard') as ctx:
+            assert ctx.get_tag(key='shard') == 0           # nothing has completed on the device yet
+        created[1].reached = True                          # first end event passed
+        assert iters.harvest() == 1
+        with monitoring.get_locked_context('shard') as ctx:
+            assert ctx.get_tag(key='shard') == 1 and ctx.get_instant_time_s(key='shard') == pytest.approx(2e-3)
+        created[5].reached = True                          # third done, second not: order is preserved, nothing reported
+        assert iters.harvest() == 0
+        assert iters.harvest(drain=True) == 2
+        with monitoring.get_locked_context('shard') as ctx:
+            assert ctx.get_tag(key='shard') == 3 and ctx.get_global_time_s(key='shard') == pytest.approx(9e-3)
+            assert ctx.get_global_work(key='shard') == 24 and ctx.get_global_accuracy(key='shard') == 72
+        with pytest.raises(KeyError):
+            iters.finish('shard')
+    finally:
+        monitoring.finish()

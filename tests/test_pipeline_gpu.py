@@ -143,7 +143,8 @@ def test_runtime_cli_adaptive_quant(policy, tmp_path):
     import subprocess
     import sys
     port = _free_port()
-    env = dict(os.environ, ADAPTIVE_QUANT=policy, SEND_CONSTRAINT='1e9', WINDOW_SIZE='2', PYTHONUNBUFFERED='1')
+    env = dict(os.environ, ADAPTIVE_QUANT=policy, SEND_CONSTRAINT='1e9', WINDOW_SIZE='2', PYTHONUNBUFFERED='1',
+               MONITORING='1' if policy == 'CONTROLLER' else '0')   # one run also with the opt-in device-timed heartbeats
     cmd = [sys.executable, os.path.join(ROOT, 'runtime.py'), None, '2', '--port', str(port), '-m',
            'facebook/deit-tiny-distilled-patch16-224', '-b', '64', '-u', '8', '-pt', '1,24,25,48', '-q', '0,0']
     procs = []
@@ -168,3 +169,6 @@ def test_runtime_cli_adaptive_quant(policy, tmp_path):
     bits = [int(b) for b in re.findall(r'Adaptive quantization \(\w+\): bitwidth1?=(\d+)', rank0)]
     assert bits, rank0[-3000:]
     assert any(0 < b < 32 for b in bits), bits
+    if policy == 'CONTROLLER':
+        for key in ('shard', 'quant_encode', 'output', 'send'):
+            assert f'{key}: Global Time' in rank0, rank0[-3000:]
