@@ -83,7 +83,7 @@ int pe_linear(const void* a, const void* w, const void* bias, const void* resid,
  * Replaces HF `eager_attention_forward` as invoked by `ViTSelfAttention`/`BertSelfAttention`
  * (reference passes no mask: `vit.py:60`, `bert.py:45`): softmax(Q K^T * head_dim^-0.5) V.
  * qkv f16 [batch*tokens, 3*heads*head_dim], columns = [Q | K | V], each head-major;
- * ctx f16 [batch*tokens, heads*head_dim] (heads merged, as `context_layer.reshape`). head_dim == 64. */
+ * ctx f16 [batch*tokens, heads*head_dim] (heads merged, as `context_layer.reshape`). head_dim 64 or 80 (ViT-Huge). */
 int pe_attention(const void* qkv, void* ctx, int batch, int tokens, int heads, int head_dim, void* stream);
 
 /* ---- f32 -> f16 cast (boundary payloads entering a mid-block stage) --------------------------- */

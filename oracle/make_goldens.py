@@ -203,9 +203,13 @@ def main():
     if sys.argv[1:] == ['adaptive']:
         golden_adaptive()
         return
+    if sys.argv[1:2] == ['tiny']:
+        for name in sys.argv[2:]:
+            golden_tiny(name)
+        return
     golden_adaptive()
     golden_quant()
-    for name in ('test/vit-tiny', 'test/deit-tiny', 'test/bert-tiny'):
+    for name in ('test/vit-tiny', 'test/deit-tiny', 'test/bert-tiny', 'test/vit-huge-tiny'):
         golden_tiny(name)
     golden_full('google/vit-base-patch16-224', 2, (2, 24, 48))
     golden_full('facebook/deit-base-distilled-patch16-224', 2, (6, 24, 48))

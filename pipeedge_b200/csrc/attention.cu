@@ -1,4 +1,5 @@
-// Unmasked multi-head self-attention, softmax(Q K^T * d^-0.5) V, for S <= ~700 tokens and d = 64.
+// Unmasked multi-head self-attention, softmax(Q K^T * d^-0.5) V, for S <= 512 tokens and head_dim d = 64 or 80
+// (80: ViT-Huge; the kernel is a template on d, any multiple of 16 would do).
 // One CTA per (query split, head, item): K and V of the head are staged once in shared memory with cp.async
 // (16-byte chunks, padded rows -> conflict-free ldmatrix, one commit group per 64-key chunk so that the first
 // chunk's maths overlaps the rest of the load); each warp owns 16 query rows and walks the keys in chunks of
@@ -15,9 +16,7 @@ namespace pe {
 
 void count_launches(int n);
 
-constexpr int kAttnD = 64;
 constexpr int kAttnKc = 64;
-constexpr int kAttnLd = kAttnD + 8;  // halves per smem row (144 bytes)
 constexpr int kAttnMaxWarps = 8;
 
 __device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
@@ -60,9 +59,11 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
 }
 
 // grid = (query splits, heads, items); block = warps * 32; each warp: 16 query rows.
+template <int kAttnD>
 __global__ void __launch_bounds__(kAttnMaxWarps * 32)
 attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ ctx, int tokens, int heads, float scale_log2e) {
   extern __shared__ __align__(16) uint8_t attn_smem[];
+  constexpr int kAttnLd = kAttnD + 8;   // halves per smem row: 144 / 176 bytes, conflict-free for ldmatrix
   pdl_launch_dependents();
   pdl_wait();
   const int nwarps = blockDim.x >> 5;
@@ -83,18 +84,20 @@ attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ ctx, int t
 
   // ---- stage Q (group 0 together with the first key chunk), then K/V chunk by chunk
   {
-    const int chunk16 = tid & 7;     // 16-byte chunk within the 128-byte head row
-    const int r0 = tid >> 3;
-    const int rstep = blockDim.x >> 3;
+    constexpr int kCpr = kAttnD / 8;   // 16-byte chunks per head row
+    const int nthreads = blockDim.x;
     const uint4 zero = make_uint4(0, 0, 0, 0);
-    for (int r = r0; r < qrows; r += rstep) {
+    for (int idx = tid; idx < qrows * kCpr; idx += nthreads) {
+      const int r = idx / kCpr, chunk16 = idx - r * kCpr;
       __half* dst = sq + r * kAttnLd + chunk16 * 8;
       if (q0 + r < tokens) cp_async_16(dst, base + static_cast<size_t>(q0 + r) * row_pitch + chunk16 * 8);
       else *reinterpret_cast<uint4*>(dst) = zero;
     }
     for (int c = 0; c < nchunks; ++c) {
-      const int kend = min(kpad, (c + 1) * kAttnKc);
-      for (int r = c * kAttnKc + r0; r < kend; r += rstep) {
+      const int kbeg = c * kAttnKc, kend = min(kpad, (c + 1) * kAttnKc);
+      for (int idx = tid; idx < (kend - kbeg) * kCpr; idx += nthreads) {
+        const int rr = idx / kCpr, chunk16 = idx - rr * kCpr;
+        const int r = kbeg + rr;
         __half* dk = sk + static_cast<size_t>(r) * kAttnLd + chunk16 * 8;
         __half* dv = sv + static_cast<size_t>(r) * kAttnLd + chunk16 * 8;
         if (r < tokens) {
@@ -239,10 +242,8 @@ attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ ctx, int t
   }
 }
 
-int attention_impl(const void* qkv, void* ctx, int batch, int tokens, int heads, int head_dim, cudaStream_t stream) {
-  PE_REQUIRE(qkv && ctx, "pe_attention: null pointer");
-  PE_REQUIRE(head_dim == kAttnD, "pe_attention: head_dim=%d unsupported (only 64)", head_dim);
-  PE_REQUIRE(batch > 0 && tokens > 0 && heads > 0, "pe_attention: bad shape");
+template <int kAttnD>
+static int launch_attention(const void* qkv, void* ctx, int batch, int tokens, int heads, cudaStream_t stream) {
   // 16-row groups -> query splits of at most 8 warps; prefer the fewest splits (K/V are staged once per CTA)
   // that still give the 148 SMs a full wave of CTAs
   const int groups = (tokens + 15) / 16;
@@ -252,21 +253,32 @@ int attention_impl(const void* qkv, void* ctx, int batch, int tokens, int heads,
   splits = (groups + warps - 1) / warps;
   const int kpad = (tokens + 15) & ~15;
   PE_REQUIRE((kpad + kAttnKc - 1) / kAttnKc <= 8, "pe_attention: tokens=%d exceeds 512", tokens);
-  const size_t smem = static_cast<size_t>(warps * 16 + 2 * kpad) * kAttnLd * sizeof(__half);
+  const size_t smem = static_cast<size_t>(warps * 16 + 2 * kpad) * (kAttnD + 8) * sizeof(__half);
   PE_REQUIRE(smem <= 227 * 1024, "pe_attention: tokens=%d exceeds the shared-memory resident K/V limit", tokens);
   static size_t configured = 0;
   if (configured == 0)
-    cudaFuncSetAttribute(attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(attention_kernel<kAttnD>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
   if (smem > configured) {
-    PE_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    PE_CUDA(cudaFuncSetAttribute(attention_kernel<kAttnD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
     configured = smem;
   }
   const dim3 grid(splits, heads, batch);
-  const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
-  PE_CUDA(launch_pdl(attention_kernel, grid, dim3(warps * 32), smem, stream, static_cast<const __half*>(qkv),
+  const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(kAttnD));
+  PE_CUDA(launch_pdl(attention_kernel<kAttnD>, grid, dim3(warps * 32), smem, stream, static_cast<const __half*>(qkv),
                      static_cast<__half*>(ctx), tokens, heads, scale_log2e));
   count_launches(1);
   return PE_OK;
+}
+
+int attention_impl(const void* qkv, void* ctx, int batch, int tokens, int heads, int head_dim, cudaStream_t stream) {
+  PE_REQUIRE(qkv && ctx, "pe_attention: null pointer");
+  PE_REQUIRE(batch > 0 && tokens > 0 && heads > 0, "pe_attention: bad shape");
+  if (head_dim == 64) return launch_attention<64>(qkv, ctx, batch, tokens, heads, stream);
+  if (head_dim == 80) return launch_attention<80>(qkv, ctx, batch, tokens, heads, stream);
+  set_error("pe_attention: head_dim=%d unsupported (64 and 80 are built)", head_dim);
+  return PE_ERR_INVALID;
 }
 
 }  // namespace pe

@@ -217,8 +217,9 @@ int pe_stage_create(const pe_stage_desc* desc, const pe_block_weights* blocks, i
              desc->family);
   PE_REQUIRE(desc->layer_start >= 1 && desc->layer_end >= desc->layer_start, "pe_stage_create: bad layer range [%d,%d]",
              desc->layer_start, desc->layer_end);
-  PE_REQUIRE(desc->hidden > 0 && desc->heads > 0 && desc->hidden % desc->heads == 0 && desc->hidden / desc->heads == 64,
-             "pe_stage_create: hidden=%d heads=%d (head_dim must be 64)", desc->hidden, desc->heads);
+  PE_REQUIRE(desc->hidden > 0 && desc->heads > 0 && desc->hidden % desc->heads == 0 &&
+                 (desc->hidden / desc->heads == 64 || desc->hidden / desc->heads == 80),
+             "pe_stage_create: hidden=%d heads=%d (head_dim must be 64 or 80)", desc->hidden, desc->heads);
   PE_REQUIRE(desc->hidden % 8 == 0 && desc->inter % 8 == 0 && desc->inter > 0, "pe_stage_create: bad hidden/inter");
   PE_REQUIRE(desc->tokens > 0 && desc->max_ubatch > 0, "pe_stage_create: bad tokens/max_ubatch");
   int rc = require_sm100();

@@ -86,10 +86,13 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilo
     return out
 
 
-def attention(qkv: torch.Tensor, batch: int, tokens: int, heads: int) -> torch.Tensor:
-    """Unmasked MHA over fused qkv f16 [batch*tokens, 3*H]; returns merged-head ctx f16 [batch*tokens, H]."""
+def attention(qkv: torch.Tensor, batch: int, tokens: int, heads: int, head_dim: int = 0) -> torch.Tensor:
+    """Unmasked MHA over fused qkv f16 [batch*tokens, 3*H]; returns merged-head ctx f16 [batch*tokens, H].
+    `head_dim` defaults to H / heads and is only checked against it."""
     _want(qkv, torch.float16, 'qkv')
     hidden = qkv.shape[-1] // 3
+    if head_dim and head_dim * heads != hidden:
+        raise ValueError(f"attention: heads={heads} x head_dim={head_dim} != hidden={hidden}")
     ctx = torch.empty((batch * tokens, hidden), dtype=torch.float16, device=qkv.device)
     check(LIB.pe_attention(qkv.data_ptr(), ctx.data_ptr(), batch, tokens, heads, hidden // heads, _stream()))
     return ctx

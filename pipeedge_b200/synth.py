@@ -63,6 +63,8 @@ MODEL_SPECS: Dict[str, ModelSpec] = {s.name: s for s in [
     ModelSpec('test/vit-tiny', 'vit', 128, 3, 2, 512, 10, image_size=64),
     ModelSpec('test/deit-tiny', 'deit', 128, 2, 2, 512, 10, image_size=64),
     ModelSpec('test/bert-tiny', 'bert', 128, 3, 2, 512, 2, vocab=1000, max_pos=64),
+    # ViT-Huge's geometry in small: head_dim 80, patch 14 (K = 588 is not a multiple of 64), odd label count
+    ModelSpec('test/vit-huge-tiny', 'vit', 160, 2, 2, 320, 11, image_size=56, patch=14),
 ]}
 
 

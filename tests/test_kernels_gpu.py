@@ -146,15 +146,17 @@ def test_linear_rejects_bad_arguments(ops):
 
 
 @pytest.mark.parametrize('batch,tokens,heads', [(2, 197, 12), (1, 128, 2), (3, 17, 2), (1, 64, 1), (1, 65, 1),
-                                                (2, 198, 12), (1, 1, 1), (1, 512, 2)])
-def test_attention(ops, batch, tokens, heads):
+                                                (2, 198, 12), (1, 1, 1), (1, 512, 2), (2, 257, 16)])
+@pytest.mark.parametrize('head_dim', [64, 80])
+def test_attention(ops, batch, tokens, heads, head_dim):
+    """head_dim 64 (ViT-B/L, DeiT, BERT) and 80 (ViT-Huge)."""
     gen = torch.Generator().manual_seed(tokens + heads)
-    hidden = heads * 64
+    hidden = heads * head_dim
     qkv = (torch.randn(batch * tokens, 3 * hidden, generator=gen) * 1.5).half()
-    q, k, v = [t.float().view(batch, tokens, heads, 64).transpose(1, 2) for t in qkv.split(hidden, dim=1)]
-    probs = F.softmax(torch.matmul(q, k.transpose(2, 3)) * 0.125, dim=-1)
+    q, k, v = [t.float().view(batch, tokens, heads, head_dim).transpose(1, 2) for t in qkv.split(hidden, dim=1)]
+    probs = F.softmax(torch.matmul(q, k.transpose(2, 3)) * head_dim ** -0.5, dim=-1)
     want = torch.matmul(probs, v).transpose(1, 2).reshape(batch * tokens, hidden)
-    got = ops.attention(qkv.cuda(), batch, tokens, heads)
+    got = ops.attention(qkv.cuda(), batch, tokens, heads, head_dim=head_dim)
     # P is rounded to fp16 before P.V and the output is fp16: 2e-3 absolute on O(1) values
     torch.testing.assert_close(got.cpu().float(), want, rtol=2e-3, atol=2e-3)
 

@@ -21,7 +21,7 @@ def _tup(g, key):
     return (torch.from_numpy(g[key + '_0']), torch.from_numpy(g[key + '_1']))
 
 
-@pytest.mark.parametrize('name', ['test/vit-tiny', 'test/deit-tiny', 'test/bert-tiny'])
+@pytest.mark.parametrize('name', ['test/vit-tiny', 'test/deit-tiny', 'test/bert-tiny', 'test/vit-huge-tiny'])
 def test_tiny_every_sublayer_boundary(name):
     """Oracle reproduces the reference after EVERY sub-layer, incl. the tuple payloads (A2)."""
     spec = MODEL_SPECS[name]
