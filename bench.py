@@ -518,11 +518,19 @@ def run_pipeline(args, spec, ubatch, seq, qbit, metric, unit, workload):
                 return wall
 
             run_phase(warmup, False, False)
+            stats0 = stage_ctx.stats()
             with ClockSampler(local) as clocks:
                 run_phase(steps, True, False)
+            stats1 = stage_ctx.stats()
             dev_ms = counter['start'].elapsed_time(counter['end'])
             ms = gather_max(dev_ms)
             launches = gather_sum(counter['launch1'] - counter['launch0'])
+            # host time per micro-batch and stage thread inside the timed phase (busy = running Python / enqueuing,
+            # wait = blocked on its queue or socket): shows which rank's host loop bounds the pipeline
+            mine = {name: {k: round((stats1[name][k] - stats0[name][k]) / steps * 1e6, 1) for k in ('busy_s', 'wait_s')}
+                    for name in stats1 if name in stats0}
+            host_stats = [None] * world
+            dist.all_gather_object(host_stats, mine)
             run_phase(warmup, False, True)
             e2e_wall = gather_max(run_phase(steps, False, True))
             if rank == 0:
@@ -546,6 +554,7 @@ def run_pipeline(args, spec, ubatch, seq, qbit, metric, unit, workload):
                     'e2e': {'value': steps * ubatch / e2e_wall, 'unit': unit, 'h2d_bytes_per_step': h2d,
                             'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_wall / steps * 1e3},
                     'gpu_launches': int(launches),
+                    'host_us_per_step': {f'rank{r}': st for r, st in enumerate(host_stats)},
                     'roofline': {'bound': 'tensor', 'kernel': 'stage GEMMs (tcgen05), pipeline aggregate',
                                  'achieved': value * total_flops / 1e12 / world,
                                  'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
