@@ -14,6 +14,6 @@ run() {  # name, timeout, pytest args...
 }
 run kernels_basic 300 tests/test_kernels_gpu.py -k "layernorm or simt or attention"
 run quant 600 tests/test_quant_gpu.py
-run kernels_tcgen05 300 tests/test_kernels_gpu.py -k "tcgen05 or resid_in_place or rejects"
+run kernels_tcgen05 300 tests/test_kernels_gpu.py -k "not (layernorm or simt or attention)"
 run shards 900 tests/test_shards_gpu.py
 exit $rc

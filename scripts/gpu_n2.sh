@@ -1,6 +1,7 @@
 #!/bin/bash
+# 2-GPU checks (run under gpurun --gpus 2): pipeline parity + adaptive-policy CLI tests, then the N=2 bench line
 mkdir -p gpurun_out
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 200 --warmup 10 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
-echo "== bench N=2 exit $?"; python -c "
-import json
-d=json.loads(open('gpurun_out/bench_n2.json').read().strip().splitlines()[-1]); print(round(d['value']), round(d['e2e']['value']), json.dumps(d['host_us_per_step']))"; grep -v Warning gpurun_out/bench_n2.err | tail -4
+timeout 1500 python -m pytest tests/test_pipeline_gpu.py -q -m gpu -p no:cacheprovider > gpurun_out/pipeline.log 2>&1
+echo "== pipeline tests: exit $?"; grep -v Warning gpurun_out/pipeline.log | tail -8
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
+echo "== bench N=2 exit $?"; tail -c 1200 gpurun_out/bench_n2.json; grep -v Warning gpurun_out/bench_n2.err | tail -4
