@@ -225,6 +225,10 @@ int pe_debug_linear_simt(const void* a, const void* w, const void* bias, const v
  * steady-state main-loop detail; 32 slots per CTA). */
 int pe_debug_gemm_trace(void* buf);
 
+/* Host-only (no device needed): the tile plan and launch geometry pe_linear would use for an [m, k] x [n, k]^T product
+ * with `epilogue`: out6 = {cluster_m, cluster_n, block_n, ring stages, tiles, CTAs}. */
+int pe_debug_gemm_plan(int m, int n, int k, int epilogue, int* out6);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,7 @@ SYMBOLS = {
     'pe_hop_wait_envelope': (c_int, [c_void_p, POINTER(c_longlong)]),
     'pe_hop_recv': (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_size_t), POINTER(c_void_p), c_int, c_void_p, c_void_p]),
     'pe_debug_gemm_trace': (c_int, [c_void_p]),
+    'pe_debug_gemm_plan': (c_int, [c_int] * 4 + [c_void_p]),
     'pe_debug_linear_simt': (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
 }
 

@@ -78,6 +78,7 @@ int quant_decode_impl(const void* codes, int items, size_t n, int bit, const voi
                       cudaStream_t stream);
 float clamp_factor(int bit, int gelu);
 void set_gemm_trace(void* buf);
+int gemm_plan_query(int m, int n, int k, int epilogue, int* out6);
 
 }  // namespace pe
 
@@ -120,6 +121,8 @@ int pe_debug_gemm_trace(void* buf) {
   pe::set_gemm_trace(buf);
   return PE_OK;
 }
+
+int pe_debug_gemm_plan(int m, int n, int k, int epilogue, int* out6) { return pe::gemm_plan_query(m, n, k, epilogue, out6); }
 
 int pe_attention(const void* qkv, void* ctx, int batch, int tokens, int heads, int head_dim, void* stream) {
   int rc = pe::require_sm100();

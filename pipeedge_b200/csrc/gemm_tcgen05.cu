@@ -700,6 +700,31 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   return PE_OK;
 }
 
+// Tile grid, ring depth and staging placement that follow from a plan (shared by the launcher and pe_debug_gemm_plan).
+static void fill_geometry(GemmParams& p, const GemmPlan& plan, int m, int n, int k) {
+  p.m = m; p.n = n; p.k = k;
+  p.block_n = plan.bn;
+  p.cm = plan.cm;
+  p.cn = plan.cn;
+  const uint32_t stage_bytes = kABytes + static_cast<uint32_t>(p.block_n) * (kBlockK * 2);
+  p.num_m_blocks = (m + kBlockM - 1) / kBlockM;
+  p.num_n_blocks = (n + p.block_n - 1) / p.block_n;
+  p.num_super_m = (p.num_m_blocks + p.cm - 1) / p.cm;
+  p.num_super_n = (p.num_n_blocks + p.cn - 1) / p.cn;
+  // One tile per CTA: the epilogue starts only after the last MMA has read the ring, so its staging may alias the
+  // ring and the whole 224 KiB go to pipeline depth (BN=256: 4 stages instead of 3). With several tiles per CTA the
+  // next tile's loads overlap the epilogue and the two need separate space.
+  const bool one_round = p.num_super_m * p.num_super_n <= max_clusters(p.cm * p.cn);
+  int stages = (one_round ? kPipeSmemBudget + kStgBytes : kPipeSmemBudget) / static_cast<int>(stage_bytes);
+  p.stages = stages > kMaxStages ? kMaxStages : (stages < 2 ? 2 : stages);
+  if (const char* cap = getenv("PE_GEMM_STAGES")) {   // tuning scripts only
+    const int c = atoi(cap);
+    if (c >= 2 && c < p.stages) p.stages = c;
+  }
+  p.stg_offset = one_round ? 0 : p.stages * static_cast<int>(stage_bytes);
+  p.num_k_blocks = (k + kBlockK - 1) / kBlockK;
+}
+
 int linear_impl(const void* a, const void* w, const void* bias, const void* resid, void* out, int m, int n, int k,
                 int epilogue, int rows_per_item, int out_item_rows, int out_row_offset, int resid_per_item,
                 int static_w, cudaStream_t stream) {
@@ -722,26 +747,7 @@ int linear_impl(const void* a, const void* w, const void* bias, const void* resi
   p.resid = static_cast<const float*>(resid);
   p.out = out;
   p.m = m; p.n = n; p.k = k;
-  p.block_n = plan.bn;
-  p.cm = plan.cm;
-  p.cn = plan.cn;
-  const uint32_t stage_bytes = kABytes + static_cast<uint32_t>(p.block_n) * (kBlockK * 2);
-  p.num_m_blocks = (m + kBlockM - 1) / kBlockM;
-  p.num_n_blocks = (n + p.block_n - 1) / p.block_n;
-  p.num_super_m = (p.num_m_blocks + p.cm - 1) / p.cm;
-  p.num_super_n = (p.num_n_blocks + p.cn - 1) / p.cn;
-  // One tile per CTA: the epilogue starts only after the last MMA has read the ring, so its staging may alias the
-  // ring and the whole 224 KiB go to pipeline depth (BN=256: 4 stages instead of 3). With several tiles per CTA the
-  // next tile's loads overlap the epilogue and the two need separate space.
-  const bool one_round = p.num_super_m * p.num_super_n <= max_clusters(p.cm * p.cn);
-  int stages = (one_round ? kPipeSmemBudget + kStgBytes : kPipeSmemBudget) / static_cast<int>(stage_bytes);
-  p.stages = stages > kMaxStages ? kMaxStages : (stages < 2 ? 2 : stages);
-  if (const char* cap = getenv("PE_GEMM_STAGES")) {   // tuning scripts only
-    const int c = atoi(cap);
-    if (c >= 2 && c < p.stages) p.stages = c;
-  }
-  p.stg_offset = one_round ? 0 : p.stages * static_cast<int>(stage_bytes);
-  p.num_k_blocks = (k + kBlockK - 1) / kBlockK;
+  fill_geometry(p, plan, m, n, k);
   p.trace = g_gemm_trace;
   p.debug_mode = 0;
   if (const char* dm = getenv("PE_GEMM_DEBUG_MODE")) p.debug_mode = atoi(dm);   // timing experiments only: results are wrong
@@ -776,6 +782,21 @@ int linear_impl(const void* a, const void* w, const void* bias, const void* resi
     case PE_EPI_TANH_F32: return launch_gemm<PE_EPI_TANH_F32>(ta, tb, tout, p, stream);
     default: set_error("pe_linear: unknown epilogue %d", epilogue); return PE_ERR_INVALID;
   }
+}
+
+// Host-only: the plan and launch geometry pe_linear would use for this shape (no device needed).
+// out6 = {cm, cn, block_n, stages, tiles, ctas}.
+int gemm_plan_query(int m, int n, int k, int epilogue, int* out6) {
+  PE_REQUIRE(out6 != nullptr && m > 0 && n > 0 && k > 0, "pe_debug_gemm_plan: bad arguments");
+  PE_REQUIRE(epilogue >= PE_EPI_F16 && epilogue <= PE_EPI_TANH_F32, "pe_debug_gemm_plan: unknown epilogue %d", epilogue);
+  const GemmPlan plan = plan_gemm(m, n, k, epilogue);
+  GemmParams p = {};
+  fill_geometry(p, plan, m, n, k);
+  const int supers = p.num_super_m * p.num_super_n, avail = max_clusters(p.cm * p.cn);
+  out6[0] = p.cm; out6[1] = p.cn; out6[2] = p.block_n; out6[3] = p.stages;
+  out6[4] = p.num_m_blocks * p.num_n_blocks;
+  out6[5] = (supers < avail ? supers : avail) * p.cm * p.cn;
+  return PE_OK;
 }
 
 // ------------------------------------------------------------------- debug reference (CUDA cores)

@@ -148,3 +148,44 @@ def test_bench_reference_arm_cli():
     assert line['impl'] == 'reference' and line['unit'] == 'images/s' and line['higher_is_better'] is True
     assert line['cpu_baseline']['kind'] == 'port' and line['e2e']['h2d_bytes_per_step'] == 0
     assert line['value'] > 0
+
+
+def _gemm_plan(m, n, k, epi):
+    import ctypes
+    from pipeedge_b200 import _lib
+    out = (ctypes.c_int * 6)()
+    _lib.check(_lib.LIB.pe_debug_gemm_plan(m, n, k, epi, out))
+    return dict(zip(('cm', 'cn', 'bn', 'stages', 'tiles', 'ctas'), out))
+
+
+def test_gemm_tile_plans_of_the_headline_shapes():
+    """`plan_gemm` is host code: the ViT-B ubatch-8 plans are the ones the sweep in profiles/r01d_plan_sweep.txt found
+    best, and the ring depth follows from the 144 / 224 KiB budgets."""
+    from pipeedge_b200 import _lib
+    m = 8 * 197
+    assert _gemm_plan(m, 2304, 768, _lib.PE_EPI_F16) == {'cm': 1, 'cn': 1, 'bn': 224, 'stages': 5, 'tiles': 143, 'ctas': 143}
+    assert _gemm_plan(m, 768, 768, _lib.PE_EPI_F32)['bn'] == 96
+    fc1 = _gemm_plan(m, 3072, 768, _lib.PE_EPI_GELU_F16)
+    assert (fc1['bn'], fc1['tiles'], fc1['ctas'], fc1['stages']) == (160, 260, 148, 4)   # two tiles per CTA: no aliasing
+    fc2 = _gemm_plan(m, 768, 3072, _lib.PE_EPI_F32)
+    assert (fc2['bn'], fc2['tiles'], fc2['stages']) == (96, 104, 8)
+
+
+def test_gemm_tile_plan_invariants():
+    """Any shape: BN a multiple of 32 in [32, 256], 2..8 stages that fit the shared-memory budget, a grid of at most
+    148 CTAs covering all tiles."""
+    import random
+    from pipeedge_b200 import _lib
+    rng = random.Random(3)
+    for _ in range(300):
+        m, n, k = rng.randint(1, 9000), rng.randint(1, 6000), 8 * rng.randint(1, 700)
+        epi = rng.choice([_lib.PE_EPI_F16, _lib.PE_EPI_GELU_F16, _lib.PE_EPI_RESID_F32, _lib.PE_EPI_F32, _lib.PE_EPI_TANH_F32])
+        p = _gemm_plan(m, n, k, epi)
+        assert p['bn'] % 32 == 0 and 32 <= p['bn'] <= 256 and p['cm'] * p['cn'] <= 8
+        assert p['tiles'] == -(-m // 128) * -(-n // p['bn'])
+        assert 1 <= p['ctas'] <= 148 and p['ctas'] <= p['tiles'] * p['cm'] * p['cn']
+        stage_bytes = 128 * 128 + p['bn'] * 128
+        budget = (144 + 80) * 1024 if p['tiles'] <= p['ctas'] else 144 * 1024
+        assert 2 <= p['stages'] <= 8 and (p['stages'] * stage_bytes <= budget or p['stages'] == 2)
+    with pytest.raises(_lib.PipeEdgeB200Error):
+        _gemm_plan(0, 8, 8, _lib.PE_EPI_F32)
