@@ -6,7 +6,6 @@ sm_100a kernels of `libpipeedge_b200.so`. Weights are read from the Google/JAX `
 loads (`vit.py:120-159,216-218`).
 """
 from collections.abc import Mapping
-from typing import Union
 import numpy as np
 import torch
 from ... import ops

@@ -20,7 +20,6 @@ import sys
 import threading
 import time
 from typing import List, Optional, Tuple, Union
-import numpy as np
 import torch
 from torch.utils.data import DataLoader, Dataset
 from pipeedge_b200 import models

@@ -2,7 +2,6 @@
 the window statistics they read) against `tests/golden/adaptive.json`, produced by running the reference's own
 `utils/{quant,controller}.py` (`oracle/make_goldens.py adaptive`)."""
 import json
-import math
 import os
 import sys
 import pytest

@@ -4,7 +4,6 @@ hooks. The reference's own lifecycle test (`test/comm/p2p/test_context.py:23-40`
 import os
 import socket
 import threading
-import pytest
 import torch
 import torch.multiprocessing as mp
 
