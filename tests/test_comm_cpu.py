@@ -97,3 +97,70 @@ def test_two_rank_pipeline_fifo_and_commands():
     (cmds,) = got['cmds']
     assert cmds[0] == (1, [[[1, 4], [5, 8]], [0, 0], 7])
     assert cmds[-1][0] == 0
+
+
+def _ragged_worker(rank, world, port, out_q):
+    """Payload layouts that change mid-stream: ragged last micro-batch, a tuple with constant host-side metadata, an
+    empty tensor, dtype changes - the envelope protocol resends the full description only when the layout changes and
+    hands out the SAME host tensors when their bytes did not change."""
+    _env(port)
+    torch.set_num_threads(1)
+    from pipeedge_b200.comm.p2p import DistP2pContext, DistP2pPipelineStage
+    stop = threading.Event()
+    done = threading.Event()
+    results = []
+    meta = torch.tensor([[7, 7]], dtype=torch.int32)          # constant across micro-batches, like the QuantPipe metadata
+    first = torch.full((4, 3), 1.0)
+    inputs = [first, first, torch.full((2, 3), 3.0),                                          # repeat, ragged tail
+              torch.zeros((0, 3)), torch.arange(6, dtype=torch.int64).view(2, 3), torch.full((4, 3), 4.0)]
+
+    def handle_results(payload):
+        results.append(payload)
+        if len(results) == len(inputs):
+            done.set()
+
+    with DistP2pContext(('gloo',), {'world_size': world, 'rank': rank},
+                        lambda cmd, tensors: stop.set() if cmd == 0 else None) as ctx:
+        if rank == 0:
+            with DistP2pPipelineStage(1, 1, lambda x: (x, meta), handle_results) as stage:
+                for x in inputs:
+                    stage.enqueue_tensor(x)
+                assert done.wait(60), "results did not arrive"
+                stage.check_workers()
+                ctx.cmd_broadcast(0)
+            out_q.put(('results', [(str(r.dtype), list(r.shape), r.tolist()) for r in results]))
+        else:
+            seen_meta = []
+
+            def work(payload):
+                x, m = payload
+                seen_meta.append(m)
+                assert m.dtype == torch.int32 and m.tolist() == [[7, 7]]
+                return x + x
+            with DistP2pPipelineStage(0, 0, work, None):
+                assert stop.wait(60), "stop command did not arrive"
+            # a payload made of the very same host tensors is not re-sent: the receiver hands out its objects again
+            out_q.put(('meta', len(seen_meta), sum(1 for a, b in zip(seen_meta, seen_meta[1:]) if a is b)))
+
+
+def test_ragged_and_changing_payload_layouts():
+    ctx = mp.get_context('spawn')
+    out_q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ragged_worker, args=(r, 2, port, out_q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(2):
+        item = out_q.get(timeout=120)
+        got[item[0]] = item[1:]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    (results,) = got['results']
+    assert [r[1] for r in results] == [[4, 3], [4, 3], [2, 3], [0, 3], [2, 3], [4, 3]]
+    assert results[0][2] == results[1][2] == [[2.0] * 3] * 4 and results[2][2] == [[6.0] * 3] * 2 and results[3][2] == []
+    assert results[4][0] == 'torch.int64' and results[4][2] == [[0, 2, 4], [6, 8, 10]]
+    assert results[5][0] == 'torch.float32' and results[5][2] == [[8.0] * 3] * 4
+    n_meta, n_same = got['meta']
+    assert n_meta == 6 and n_same == 1      # payloads 0 and 1 were the same objects on the sender: received once
