@@ -20,3 +20,8 @@ def forward_pre_hook_to_device(_module, inputs) -> Union[Tuple[torch.Tensor], Tu
 def forward_hook_to_cpu(_module, _inputs, outputs) -> Union[torch.Tensor, Tuple[torch.Tensor]]:
     """Reference: move tensors to the CPU. Here: identity (payloads stay in HBM for the NCCL hop)."""
     return outputs
+
+
+# identities on every path, so the native pipeline may ignore them (see comm/p2p/_native.py: hook_is_native)
+forward_pre_hook_to_device._pe_native = True   # pylint: disable=protected-access
+forward_hook_to_cpu._pe_native = True          # pylint: disable=protected-access

@@ -31,7 +31,7 @@ extern "C" {
 #define PE_ERR_DEVICE (-3)  /* no sm_100 device */
 #define PE_ERR_NOMEM (-4)
 
-#define PE_ABI_VERSION 1
+#define PE_ABI_VERSION 2
 
 /* Model family: selects pre-LN (ViT/DeiT: reference `vit.py:55-70`, `deit.py:54-69`) or post-LN
  * (BERT: `bert.py:41-52`) block structure. */
@@ -167,6 +167,12 @@ int pe_stage_destroy(pe_stage* stage);
  * (ubatch, pointers) tuple is captured into a CUDA graph on first use and replayed afterwards. */
 int pe_stage_forward(pe_stage* stage, const void* in0, const void* in1, void* out0, void* out1, int ubatch,
                      int use_graph, void* stream);
+/* OR-able into `use_graph` (eager launches only, i.e. bit 0 clear): a stage that ends on an output projection / FC2
+ * (`vit.py:62-64,69`) leaves its final residual add to the consumer; pe_stage_deferred then returns the two addends
+ * (f32 [ubatch, S, H] each, library / caller owned, valid until the next forward), or NULLs when nothing was deferred
+ * and the result is in out0 as usual. The link's send kernel (pe_link_put) adds while it reads. */
+#define PE_STAGE_DEFER_ADD 2
+int pe_stage_deferred(const pe_stage* stage, const void** a, const void** b);
 /* One EAGER forward with a CUDA event after every kernel: ms_out[i] = device time of kernel i,
  * kinds_out[i] = PE_KERNEL_* (up to `capacity` entries, *n_out = kernels launched). Synchronises `stream`. */
 #define PE_KERNEL_CAST 0
@@ -199,7 +205,76 @@ int pe_bert_embed(const void* ids, const void* pos_ids, const void* word, const 
                   const void* gamma, const void* beta, float eps, void* out, int batch, int seq, int hidden,
                   void* stream);
 
-/* ---- Inter-stage hop (native fast path) --------------------------------------------------------
+/* ---- Peer-memory links: the inter-stage hop as NVLink stores + device-polled flags -------------------
+ * Replaces `TensorSendThread.run` / `TensorRecvThread.run` + `_send_tensor` / `_recv_tensor`
+ * (`p2p/__init__.py:96-258`) and, on quantised hops, `forward_hook_quant_encode` /
+ * `forward_pre_hook_quant_decode` (`runtime.py:73-119`) around them. A link is a ring of slots in the CONSUMER's
+ * HBM, mapped into the producer with cudaIpc; per slot a `full` counter (raised by the producer's kernel after its
+ * stores) and a `free` counter (raised by the consumer's kernel after its reads), both polled on the devices. The
+ * kernels find their slot through device-resident sequence counters, so they take no per-payload arguments and a
+ * stage's get -> blocks -> put sequence replays as one CUDA graph. Host side: one 16-byte ticket per payload on the
+ * hop's Unix-domain socket `fd` (owned by the caller). Wire format per tensor: f32 values (f16 with
+ * PIPEEDGE_WIRE_F16=1) or, for bit > 0, the reference's packed codes (`basic_op.py:38-55`: floor(32/bit) codes per
+ * little-endian uint32, LSB first) + per-item f32 scale / shift in the slot header. */
+typedef struct pe_link pe_link;
+/* Peer link over `fd`; blocks until the other end has called it too. The producer picks the geometry
+ * (`slot_payload_bytes` per slot, `n_slots` in [2,8]); the consumer passes 0, 0. */
+int pe_link_open(int fd, int is_producer, size_t slot_payload_bytes, int n_slots, pe_link** out);
+/* Both ends in this process (one-rank pipelines, tests). */
+int pe_link_open_local(size_t slot_payload_bytes, int n_slots, pe_link** out);
+/* Consumer end fed by the host with pe_link_feed (the data rank's inputs, `devices.forward_pre_hook_to_device`). */
+int pe_link_open_host(size_t slot_payload_bytes, int n_slots, pe_link** out);
+int pe_link_close(pe_link* link);
+size_t pe_link_slot_bytes(const pe_link* link);
+/* Producer: ship a payload of one or two tensors, x_i = a_i (+ b_i), each f32 [items, n_i]; a1 == NULL for one tensor.
+ * bit == 0: raw values; bit in [1,16]: QuantPipe (`clamp` = PE_CLAMP_*). For bit in {2,4,8,16} and n % 16 == 0 this
+ * is ONE kernel per tensor: statistics -> grid barrier -> thresholds -> quantise + pack + peer stores, the fp32 slice
+ * held in shared memory in between; other widths run the stand-alone quant kernels and one shipping kernel. */
+int pe_link_put(pe_link* link, const void* a0, const void* b0, size_t n0, const void* a1, const void* b1, size_t n1,
+                int items, int bit, int clamp, void* stream);
+/* The fused encode-and-send of one tensor under the name SURVEY.md 8(b) gives it (= pe_link_put with bit > 0). */
+int pe_quant_encode_send(pe_link* link, const void* x, const void* skip, int items, size_t n, int bit, int clamp,
+                         void* stream);
+/* Consumer: wait for the next payload (on the device), copy / dequantise (`tensor_decode_outerdim`,
+ * `basic_op.py:146-176`) it into dst0 (/ dst1) as f32 [items, n0] (/ [items, n1]) and release the slot. The payload's
+ * description must match (items, n0, n1) or the kernel traps and pe_link_check reports it. */
+int pe_link_get(pe_link* link, void* dst0, void* dst1, int items, size_t n0, size_t n1, void* stream);
+int pe_link_get_raw(pe_link* link, void* dst, size_t bytes, void* stream);   /* host-fed links */
+/* Host-fed link: copy the next payload into the ring on `copy_stream` (blocks on the host while the ring is full). */
+int pe_link_feed(pe_link* link, const void* src, size_t bytes, int src_is_host, void* copy_stream);
+int pe_link_ticket_send(pe_link* link, long long a, long long b);
+int pe_link_ticket_recv(pe_link* link, long long* out2);   /* blocks; 1 = the peer closed */
+int pe_link_check(pe_link* link);                          /* PE_OK, or the protocol error a link kernel reported */
+int pe_link_debug_read(pe_link* link, unsigned long long seq, size_t offset, void* host_dst, size_t bytes);
+#define PE_LINK_HEADER_BYTES 16384   /* slot = [header | payload]; scale f32[512] of tensor t at 256 + 4096 t, shift 2048 later */
+
+/* ---- Per-rank stage loop ---------------------------------------------------------------------------
+ * Replaces `TensorWorkThread.run` and the queue hand-offs of `DistP2pPipelineStage` (`p2p/__init__.py:261-295,
+ * 373-394,442-450`): a stage's micro-batch (link get -> kernels -> link put) is captured once into a CUDA graph;
+ * per micro-batch the host reads a ticket, launches the graph and writes a ticket - in C, GIL released. */
+typedef struct pe_pipe pe_pipe;
+int pe_pipe_create(pe_link* in, pe_link* out, pe_link* res, pe_pipe** out_pipe);
+int pe_pipe_destroy(pe_pipe* pipe);
+void* pe_pipe_stream(pe_pipe* pipe);
+void* pe_pipe_copy_stream(pe_pipe* pipe);
+int pe_pipe_has_graph(pe_pipe* pipe, int ubatch, long long dim1);
+int pe_pipe_capture_begin(pe_pipe* pipe, int ubatch, long long dim1, void* dst0, void* dst1, size_t n0, size_t n1,
+                          size_t raw_bytes);
+int pe_pipe_capture_end(pe_pipe* pipe, const void* a0, const void* b0, size_t n0, const void* a1, const void* b1,
+                        size_t n1, int items, int bit, int clamp, int* kernels);
+int pe_pipe_capture_abort(pe_pipe* pipe);
+int pe_pipe_invalidate(pe_pipe* pipe);
+int pe_pipe_submit(pe_pipe* pipe, const void* src, size_t bytes, int src_is_host, int ubatch, long long dim1);
+int pe_pipe_close_input(pe_pipe* pipe);
+int pe_pipe_run(pe_pipe* pipe, long long* need2);   /* 1 = closed, 2 = graph needed for need2 = {ubatch, dim1} */
+int pe_pipe_set_out_dim(pe_pipe* pipe, long long n);   /* last stage: result elements per item, sent with its tickets */
+int pe_pipe_next_result(pe_pipe* pipe, void** host_ptr, int* items, size_t* n);   /* 1 = closed */
+int pe_pipe_sync(pe_pipe* pipe);
+int pe_pipe_timing_reset(pe_pipe* pipe);
+int pe_pipe_timing(pe_pipe* pipe, float* compute_ms, float* results_ms, unsigned long long* launches,
+                   unsigned long long* kernels);
+
+/* ---- Inter-stage hop over NCCL (generic payloads) -----------------------------------------------
  * Replaces `TensorSendThread.run` / `TensorRecvThread.run` + `_send_tensor` / `_recv_tensor`
  * (`p2p/__init__.py:96-258`) for the device tensors of a payload: one call per payload and side, over a
  * dedicated 2-rank NCCL communicator per directed hop; `fd` is the hop's connected Unix-domain socket (owned by

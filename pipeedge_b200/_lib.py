@@ -5,7 +5,7 @@ machine without an sm_100 GPU fails with `PipeEdgeB200Error` (PE_ERR_DEVICE).
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_longlong, c_size_t, c_uint64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_longlong, c_size_t, c_uint64, c_ulonglong, c_void_p
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, 'libpipeedge_b200.so')
@@ -15,6 +15,9 @@ PE_FAMILY = {'vit': 0, 'deit': 1, 'bert': 2}
 PE_EPI_F16, PE_EPI_GELU_F16, PE_EPI_RESID_F32, PE_EPI_F32, PE_EPI_TANH_F32 = range(5)
 PE_EPI_STATIC_W = 0x100   # OR-able flag: W is a model weight (not produced by pending work on the stream)
 PE_CLAMP_NONE, PE_CLAMP_AUTO, PE_CLAMP_LAPLACE, PE_CLAMP_GELU = range(4)
+PE_STAGE_DEFER_ADD = 2        # OR-able into pe_stage_forward's use_graph (eager only)
+PE_LINK_HEADER_BYTES = 16384
+PE_ABI_VERSION = 2
 
 
 class PipeEdgeB200Error(RuntimeError):
@@ -56,6 +59,7 @@ SYMBOLS = {
     'pe_stage_profile': (c_int, [c_void_p] * 5 + [c_int, c_void_p, POINTER(c_float), POINTER(c_int), c_int,
                                  POINTER(c_int)]),
     'pe_stage_kernel_count': (c_int, [c_void_p]),
+    'pe_stage_deferred': (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p)]),
     'pe_patch_embed': (c_int, [c_void_p] * 7 + [c_int] * 6 + [c_void_p]),
     'pe_bert_embed': (c_int, [c_void_p] * 7 + [c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
     'pe_hop_available': (c_int, []),
@@ -64,6 +68,40 @@ SYMBOLS = {
     'pe_hop_send': (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_size_t), c_int, c_void_p, c_void_p, c_void_p, c_int]),
     'pe_hop_wait_envelope': (c_int, [c_void_p, POINTER(c_longlong)]),
     'pe_hop_recv': (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_size_t), POINTER(c_void_p), c_int, c_void_p, c_void_p]),
+    'pe_link_open': (c_int, [c_int, c_int, c_size_t, c_int, POINTER(c_void_p)]),
+    'pe_link_open_local': (c_int, [c_size_t, c_int, POINTER(c_void_p)]),
+    'pe_link_open_host': (c_int, [c_size_t, c_int, POINTER(c_void_p)]),
+    'pe_link_close': (c_int, [c_void_p]),
+    'pe_link_slot_bytes': (c_size_t, [c_void_p]),
+    'pe_link_put': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int,
+                            c_void_p]),
+    'pe_quant_encode_send': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_size_t, c_int, c_int, c_void_p]),
+    'pe_link_get': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_size_t, c_size_t, c_void_p]),
+    'pe_link_get_raw': (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    'pe_link_feed': (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    'pe_link_ticket_send': (c_int, [c_void_p, c_longlong, c_longlong]),
+    'pe_link_ticket_recv': (c_int, [c_void_p, POINTER(c_longlong)]),
+    'pe_link_check': (c_int, [c_void_p]),
+    'pe_link_debug_read': (c_int, [c_void_p, c_ulonglong, c_size_t, c_void_p, c_size_t]),
+    'pe_pipe_create': (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_void_p)]),
+    'pe_pipe_destroy': (c_int, [c_void_p]),
+    'pe_pipe_stream': (c_void_p, [c_void_p]),
+    'pe_pipe_copy_stream': (c_void_p, [c_void_p]),
+    'pe_pipe_has_graph': (c_int, [c_void_p, c_int, c_longlong]),
+    'pe_pipe_capture_begin': (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_size_t, c_size_t, c_size_t]),
+    'pe_pipe_capture_end': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_int, c_int,
+                                    c_int, POINTER(c_int)]),
+    'pe_pipe_capture_abort': (c_int, [c_void_p]),
+    'pe_pipe_invalidate': (c_int, [c_void_p]),
+    'pe_pipe_set_out_dim': (c_int, [c_void_p, c_longlong]),
+    'pe_pipe_submit': (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_longlong]),
+    'pe_pipe_close_input': (c_int, [c_void_p]),
+    'pe_pipe_run': (c_int, [c_void_p, POINTER(c_longlong)]),
+    'pe_pipe_next_result': (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int), POINTER(c_size_t)]),
+    'pe_pipe_sync': (c_int, [c_void_p]),
+    'pe_pipe_timing_reset': (c_int, [c_void_p]),
+    'pe_pipe_timing': (c_int, [c_void_p, POINTER(c_float), POINTER(c_float), POINTER(c_ulonglong),
+                               POINTER(c_ulonglong)]),
     'pe_debug_gemm_trace': (c_int, [c_void_p]),
     'pe_debug_gemm_plan': (c_int, [c_int] * 4 + [c_void_p]),
     'pe_debug_linear_simt': (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),

@@ -12,7 +12,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, 'csrc')
 OBJ_DIR = os.path.join(CSRC, 'build')
 LIB_PATH = os.path.join(PKG_DIR, 'libpipeedge_b200.so')
-SOURCES = ['api.cu', 'gemm_tcgen05.cu', 'layernorm.cu', 'attention.cu', 'quant.cu', 'stage.cu', 'edges.cu', 'hop.cu']
+SOURCES = ['api.cu', 'gemm_tcgen05.cu', 'layernorm.cu', 'attention.cu', 'quant.cu', 'stage.cu', 'edges.cu', 'hop.cu', 'link.cu', 'pipe.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 # -fmad=false is NOT set globally: the quantisation kernels use explicit _rn intrinsics where bit-exactness
 # matters, everything else may contract.
@@ -23,7 +23,8 @@ FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-li
 def _newer(src: str, dst: str) -> bool:
     if not os.path.exists(dst):
         return True
-    deps = [src, os.path.join(CSRC, 'common.cuh'), os.path.join(PKG_DIR, '..', 'include', 'pipeedge_b200.h')]
+    deps = [src, os.path.join(PKG_DIR, '..', 'include', 'pipeedge_b200.h')] + \
+        [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith('.cuh')]
     return any(os.path.getmtime(d) > os.path.getmtime(dst) for d in deps)
 
 

@@ -791,7 +791,44 @@ class DistP2pPipelineStage:
         self._initialized = False
         self._queues = {}
         self._threads = {}
+        self._args = (rank_src, rank_dst, work_cb, results_cb)
+        self._native = None            # _native.NativeStage once init() has chosen the native pipeline
+        self._native_world = False     # every rank agreed on it (then shutdown ends with a drain barrier everywhere)
         self._create_stage(rank_src, rank_dst, work_cb, results_cb)
+
+    # ------------------------------------------------------------------ native pipeline selection
+    def _native_capable(self) -> bool:
+        """Whether THIS rank's role can run on the native pipeline (csrc/pipe.cu): a B200 shard as the worker, hooks
+        that the link kernels account for, the reference's ring topology with the data rank on the first stage."""
+        rank_src, rank_dst, work_cb, results_cb = self._args
+        if os.environ.get('PIPEEDGE_NATIVE', '1') == '0' or not torch.cuda.is_available():
+            return False
+        if rank_src is None and rank_dst is None and work_cb is None and results_cb is None:
+            return True    # idle rank: neutral
+        try:
+            from ._native import shard_is_native   # pylint: disable=import-outside-toplevel
+        except ImportError:
+            return False
+        if work_cb is None or not shard_is_native(work_cb):
+            return False
+        if any(thr._pre_hooks or thr._post_hooks or getattr(thr, '_timing_hooks', None)   # pylint: disable=protected-access
+               for thr in self._threads.values() if isinstance(thr, AbstractTensorExchangeThread)):
+            return False   # user hooks run on the Python exchange threads
+        if (rank_src is None) != (rank_dst is None):
+            return False
+        if results_cb is not None and not work_cb.shard_config.is_first:
+            return False
+        return True
+
+    def _choose_native(self) -> bool:
+        capable = self._native_capable()
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            if os.environ.get('PIPEEDGE_NATIVE', '1') == '0' or not torch.cuda.is_available():
+                return False   # the same on every rank: nobody enters the vote
+            vote = torch.tensor([1 if capable else 0], dtype=torch.int)
+            dist.all_reduce(vote, op=dist.ReduceOp.MIN)    # control plane (Gloo); every rank builds a stage object
+            return bool(vote[0])
+        return capable and self._args[0] is None and self._args[1] is None
 
     def _create_stage(self, rank_src, rank_dst, work_cb, results_cb):
         depth = queue_depth()
@@ -812,9 +849,18 @@ class DistP2pPipelineStage:
             self._threads['recv'] = TensorRecvThread(queue_in, rank_src)
 
     def init(self) -> None:
-        """Start the threads."""
+        """Start the threads - or, when every rank runs a B200 shard with hooks the link kernels account for, the
+        native pipeline (one CUDA graph per micro-batch, stage loop in C; `_native.py`)."""
         assert not self._initialized
         self._initialized = True
+        if self._choose_native():
+            self._native_world = True
+            rank_src, rank_dst, work_cb, results_cb = self._args
+            if work_cb is not None:
+                from ._native import NativeStage   # pylint: disable=import-outside-toplevel
+                self._native = NativeStage(rank_src, rank_dst, work_cb, results_cb)
+                self._native.init(DistP2pContext.connect_to, DistP2pContext.accept_from)
+            return
         # Open this rank's hops in ascending order of the hop's SENDER rank before any thread runs. Opening blocks
         # until the peer joins (socket accept, NCCL communicator init); a global order rules out circular waits.
         hops = []
@@ -831,6 +877,13 @@ class DistP2pPipelineStage:
         """Stop and join the threads."""
         assert self._initialized
         self._initialized = False
+        if self._native_world:
+            if self._native is not None:
+                self._native.shutdown()
+            elif dist.is_initialized() and dist.get_world_size() > 1:
+                from ._native import drain_barrier   # pylint: disable=import-outside-toplevel
+                drain_barrier()    # idle rank: the stages' drain barrier counts every rank
+            return
         # workers drain first, then the sender closes its hop (which lets the peer's receiver finish), then our
         # receiver waits for the upstream sender's closing message
         for name in ('work', 'res', 'send', 'recv'):
@@ -841,24 +894,28 @@ class DistP2pPipelineStage:
 
     def register_recv_pre_hook(self, hook: Callable[..., None], args: tuple) -> None:
         """Register a pre hook for tensor receive with signature: `hook(*args)`."""
+        self._no_hooks_on_native()
         thr = self._threads.get('recv')
         if thr is not None:
             thr.register_pre_hook(hook, args)
 
     def register_recv_post_hook(self, hook: Callable[..., None], args: tuple) -> None:
         """Register a post hook for tensor receive with signature: `hook(tensors, *args)`."""
+        self._no_hooks_on_native()
         thr = self._threads.get('recv')
         if thr is not None:
             thr.register_post_hook(hook, args)
 
     def register_send_pre_hook(self, hook: Callable[..., None], args: tuple) -> None:
         """Register a pre hook for tensor send with signature: `hook(*args)`."""
+        self._no_hooks_on_native()
         thr = self._threads.get('send')
         if thr is not None:
             thr.register_pre_hook(hook, args)
 
     def register_send_post_hook(self, hook: Callable[..., None], args: tuple) -> None:
         """Register a post hook for tensor send with signature: `hook(tensors, *args)`."""
+        self._no_hooks_on_native()
         thr = self._threads.get('send')
         if thr is not None:
             thr.register_post_hook(hook, args)
@@ -868,9 +925,26 @@ class DistP2pPipelineStage:
         around the hop's NCCL sends). The send post hook above fires when a send is enqueued, not when it has
         finished, so bandwidth-driven policies (`runtime.py:121-216` in the reference) read this instead. No
         reference equivalent: there the blocking send itself is timed on the host."""
+        self._no_hooks_on_native()
         thr = self._threads.get('send')
         if thr is not None:
             thr.register_timing_hook(hook, args)
+
+    def _no_hooks_on_native(self) -> None:
+        if self._native_world:
+            raise RuntimeError("the native pipeline is running: register exchange hooks BEFORE init() (they select the "
+                               "Python exchange threads) or set PIPEEDGE_NATIVE=0")
+
+    @property
+    def native(self):
+        """The `_native.NativeStage` driving this rank, or None (Python threads / idle rank)."""
+        return self._native
+
+    def prepare(self, ubatch: int, dim1: int = 0) -> None:
+        """Optional: capture the stage's CUDA graph for micro-batches of `ubatch` items (`dim1`: BERT sequence length)
+        before the first payload arrives. No-op on the Python-thread path. Call before any traffic."""
+        if self._native is not None:
+            self._native.prepare(ubatch, dim1)
 
     def __enter__(self):
         self.init()
@@ -881,10 +955,15 @@ class DistP2pPipelineStage:
 
     def stats(self) -> dict:
         """Per-thread host time: blocked waiting (`wait_s`) vs working (`busy_s`) and items handled."""
+        if self._native_world:
+            return {}
         return {name: dict(thr.stats) for name, thr in self._threads.items() if hasattr(thr, 'stats')}
 
     def check_workers(self) -> None:
         """Re-raise an exception that killed a worker thread (the reference would hang instead)."""
+        if self._native is not None:
+            self._native.check()
+            return
         for thr in self._threads.values():
             exc = getattr(thr, 'exception', None)
             if exc is not None:
@@ -893,6 +972,9 @@ class DistP2pPipelineStage:
     def enqueue_tensor(self, tensor: torch.Tensor) -> None:
         """Insert data into the pipeline; blocks while the inbound queue is full (`p2p/__init__.py:442-450`)."""
         assert self._initialized
+        if self._native is not None:
+            self._native.enqueue(tensor)
+            return
         queue_in = self._queues['in']
         with queue_in.condition:
             while queue_in.full():

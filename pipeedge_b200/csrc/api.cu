@@ -38,6 +38,7 @@ bool pdl_enabled() {
 }
 
 void count_launches(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
+uint64_t launch_count_now() { return g_launches.load(std::memory_order_relaxed); }
 
 // The kernels use tcgen05 / TMEM / TMA PTX that exists only on sm_100: refuse anything else loudly.
 int require_sm100() {

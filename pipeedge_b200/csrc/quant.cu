@@ -8,14 +8,13 @@
 
 #include "../../include/pipeedge_b200.h"
 #include "common.cuh"
+#include "quant_dev.cuh"
 
 namespace pe {
 
 void count_launches(int n);
 
-constexpr int kQMaxChunks = 64;      // partial-reduction chunks per item
 constexpr int kQStatThreads = 256;
-constexpr int kQPartialDoubles = 5;  // min, max, sum, sumsq, sumsq of fp32-rounded squares
 
 // ------------------------------------------------------------------ Lambert W (host, fp64)
 static double lambert_w0(double z) {
@@ -38,12 +37,6 @@ float clamp_factor(int bit, int gelu) {
 }
 
 // ------------------------------------------------------------------ pass 1: statistics
-__device__ __forceinline__ double warp_sum_d(double v) {
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-  return v;
-}
-
 __global__ void __launch_bounds__(kQStatThreads)
 quant_stats_kernel(const float* __restrict__ x, size_t n, int chunks, double* __restrict__ partials) {
   const int item = blockIdx.y, chunk = blockIdx.x;
@@ -139,25 +132,9 @@ __global__ void quant_finalize_kernel(double* partials, int items, int chunks, s
       gmin = fmin(gmin, p0[0]);
       gs += p0[2]; gss += p0[3]; gss32 += p0[4];
     }
-    float alpha = INFINITY;
-    if (clamp != PE_CLAMP_NONE) {
-      const double cnt = static_cast<double>(items) * static_cast<double>(n);
-      float variance, factor;
-      const bool laplace = clamp == PE_CLAMP_LAPLACE || (clamp == PE_CLAMP_AUTO && gmin < 0.2);
-      if (laplace) {
-        // torch.var(x, unbiased=False) on CPU: fp64 accumulation, result rounded to fp32 (clamp_op.py:30)
-        const double mean = gs / cnt;
-        double var_d = gss / cnt - mean * mean;
-        if (var_d < 0.0) var_d = 0.0;
-        variance = static_cast<float>(var_d);
-        factor = factor_laplace;
-      } else {
-        // 2 * sum(x^2) / numel with fp32 squares and an fp32 sum (clamp_op.py:16)
-        variance = __fdiv_rn(__fmul_rn(2.0f, static_cast<float>(gss32)), static_cast<float>(cnt));
-        factor = factor_gelu;
-      }
-      alpha = __fmul_rn(factor, __fsqrt_rn(__fmul_rn(0.5f, variance)));
-    }
+    // clamp_op.py:11-33 (see clamp_alpha in quant_dev.cuh; the fused send kernel of link.cu shares it)
+    const float alpha = clamp_alpha(clamp, gmin, gs, gss, gss32, static_cast<double>(items) * static_cast<double>(n),
+                                    factor_laplace, factor_gelu);
     s_alpha = alpha;
     hdr->alpha = alpha;
     if (alpha_out != nullptr) *alpha_out = alpha;
@@ -174,12 +151,6 @@ __global__ void quant_finalize_kernel(double* partials, int items, int chunks, s
 }
 
 // ------------------------------------------------------------------ pass 2: quantise + pack
-__device__ __forceinline__ uint32_t quant_code(float x, float alpha, float shift, float scale, float levels) {
-  const float xc = fminf(fmaxf(x, -alpha), alpha);
-  const float r = __fdiv_rn(__fsub_rn(xc, shift), scale);  // basic_op.py:127-130
-  return static_cast<uint32_t>(rintf(__fmul_rn(levels, r)));  // np.around, then astype(uint32)
-}
-
 // Fast path: bit in {2,4,8,16} and n % 16 == 0. One thread = 16 consecutive elements (4 x float4 in,
 // 16*bit/32 words out as one vector store).
 template <int BIT>
@@ -264,7 +235,7 @@ quant_decode_kernel(const uint32_t* __restrict__ codes, size_t n, int bit, size_
   const double levels = static_cast<double>(mask);
   const bool use_lut = bit <= 12;
   if (use_lut) {
-    for (uint32_t c = threadIdx.x; c <= mask; c += blockDim.x) lut[c] = static_cast<float>(static_cast<double>(c) / levels);
+    for (uint32_t c = threadIdx.x; c <= mask; c += blockDim.x) lut[c] = dequant_unit(c, levels);
     __syncthreads();
   }
   const float sc = scale[item], sh = shift[item];
@@ -278,8 +249,8 @@ quant_decode_kernel(const uint32_t* __restrict__ codes, size_t n, int bit, size_
       const size_t e = e0 + j;
       if (e >= n) break;
       const uint32_t c = (word >> (j * bit)) & mask;
-      const float v = use_lut ? lut[c] : static_cast<float>(static_cast<double>(c) / levels);
-      oi[e] = __fadd_rn(__fmul_rn(v, sc), sh);  // basic_op.py:163: two fp32 roundings
+      const float v = use_lut ? lut[c] : dequant_unit(c, levels);
+      oi[e] = dequant_value(v, sc, sh);  // basic_op.py:163: two fp32 roundings
     }
   }
 }

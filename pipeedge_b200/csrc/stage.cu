@@ -49,6 +49,8 @@ struct pe_stage {
   __half* inter16 = nullptr;
   float* t32 = nullptr;
   int kernels_last = 0;
+  const void* defer_a = nullptr;   // PE_STAGE_DEFER_ADD: the stage's output is defer_a + defer_b, left to the consumer
+  const void* defer_b = nullptr;
   cudaStream_t capture_stream = nullptr;  // private stream the kernel sequence is captured on
   typedef std::tuple<int, const void*, const void*, void*, void*> Key;
   struct Cached {
@@ -96,7 +98,7 @@ static int lin(const void* a, const void* w, const void* b, const void* resid, v
 
 // Enqueue the kernel sequence of one forward on `stream`. Returns the number of kernels in *count.
 static int enqueue(pe_stage* st, const void* in0, const void* in1, void* out0, void* out1, int ubatch,
-                   cudaStream_t stream, int* count, Prof* prof = nullptr) {
+                   cudaStream_t stream, int* count, Prof* prof = nullptr, bool defer_add = false) {
   const pe_stage_desc& d = st->d;
   const int H = d.hidden, I = d.inter, S = d.tokens;
   const int M = ubatch * S;
@@ -174,7 +176,13 @@ static int enqueue(pe_stage* st, const void* in0, const void* in1, void* out0, v
       }
     }
   }
-  if (pending) {   // the stage ends on an output projection / FC2: materialise the sum
+  st->defer_a = st->defer_b = nullptr;
+  if (pending && defer_add && !out_tuple) {
+    // the stage ends on an output projection / FC2 and its consumer (the link's send kernel) adds while it reads
+    st->defer_a = st->t32;
+    st->defer_b = skip;
+    pending = false;
+  } else if (pending) {   // ... otherwise materialise the sum
     PE_K(PE_KERNEL_CAST, add_impl(st->t32, skip, resid_dest, static_cast<size_t>(M) * H, stream));
     x = resid_dest; skip = nullptr; pending = false;
   }
@@ -287,7 +295,8 @@ int pe_stage_forward(pe_stage* st, const void* in0, const void* in1, void* out0,
   PE_REQUIRE(ubatch > 0 && ubatch <= st->d.max_ubatch, "pe_stage_forward: ubatch=%d outside [1,%d]", ubatch,
              st->d.max_ubatch);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  if (!use_graph) return enqueue(st, in0, in1, out0, out1, ubatch, stream, &st->kernels_last);
+  if ((use_graph & 1) == 0)
+    return enqueue(st, in0, in1, out0, out1, ubatch, stream, &st->kernels_last, nullptr, (use_graph & PE_STAGE_DEFER_ADD) != 0);
 
   pe_stage::Cached& c = st->graphs[pe_stage::Key(ubatch, in0, in1, out0, out1)];
   if (c.exec != nullptr) {
@@ -302,9 +311,13 @@ int pe_stage_forward(pe_stage* st, const void* in0, const void* in1, void* out0,
   }
   // second use: capture the same sequence on the stage's private stream (the caller's stream may be the
   // legacy default stream, which cannot be captured), instantiate, then launch into the caller's stream
-  if (st->graphs.size() > 64) {  // pointers that never repeat would grow the cache without bound
-    for (auto& kv : st->graphs)
-      if (kv.second.exec != nullptr && &kv.second != &c) { cudaGraphExecDestroy(kv.second.exec); kv.second.exec = nullptr; }
+  if (st->graphs.size() > 64) {  // pointers that never repeat would grow the cache without bound: start over
+    const pe_stage::Key mine(ubatch, in0, in1, out0, out1);
+    for (auto it = st->graphs.begin(); it != st->graphs.end();) {
+      if (it->first == mine) { ++it; continue; }
+      if (it->second.exec != nullptr) cudaGraphExecDestroy(it->second.exec);
+      it = st->graphs.erase(it);
+    }
   }
   if (st->capture_stream == nullptr) PE_CUDA(cudaStreamCreateWithFlags(&st->capture_stream, cudaStreamNonBlocking));
   cudaGraph_t graph = nullptr;
@@ -357,5 +370,13 @@ int pe_stage_profile(pe_stage* st, const void* in0, const void* in1, void* out0,
 }
 
 int pe_stage_kernel_count(const pe_stage* st) { return st == nullptr ? 0 : st->kernels_last; }
+
+int pe_stage_deferred(const pe_stage* st, const void** a, const void** b) {
+  using namespace pe;
+  PE_REQUIRE(st != nullptr && a != nullptr && b != nullptr, "pe_stage_deferred: null pointer");
+  *a = st->defer_a;
+  *b = st->defer_b;
+  return PE_OK;
+}
 
 }  // extern "C"

@@ -30,6 +30,8 @@ class GpuTransformerShard(ModuleShard):
         super().__init__(config, shard_config)
         self.use_cuda_graph = False
         self.num_slots = 4
+        self._static = False       # native pipeline capture: single persistent buffers, eager launches, deferred add
+        self._deferred = None      # (a, b) device addresses when the last static forward deferred its final add
         self._slot = 0
         self._rings = {}
         self._copy_stream = None
@@ -103,15 +105,27 @@ class GpuTransformerShard(ModuleShard):
 
     def _ring(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
         """Persistent buffer `name` of the current slot (allocated on first use per shape)."""
-        key = (name, tuple(shape), dtype, self._slot)
+        key = (name, tuple(shape), dtype, 0 if self._static else self._slot)
         buf = self._rings.get(key)
         if buf is None:
             buf = torch.empty(tuple(shape), dtype=dtype, device=self.stage.device)
             self._rings[key] = buf
         return buf
 
+    @property
+    def persistent(self) -> bool:
+        """Whether forward outputs live in persistent buffers (either graph mode)."""
+        return self.use_cuda_graph or self._static
+
+    def _tmp(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
+        """A small edge / head buffer: persistent while the native pipeline captures (`_static`), fresh otherwise (the
+        per-call graph mode hands results to queues that may still hold them `num_slots` forwards later)."""
+        if self._static:
+            return self._ring(name, shape, dtype)
+        return torch.empty(tuple(shape), dtype=dtype, device=self.stage.device)
+
     def _stage_out(self, ubatch: int) -> Optional[Tuple[torch.Tensor, Optional[torch.Tensor]]]:
-        if not self.use_cuda_graph:
+        if not self.persistent:
             return None
         s0, s1 = self.stage.out_shapes(ubatch)
         return self._ring('out0', s0), (None if s1 is None else self._ring('out1', s1))
@@ -120,15 +134,89 @@ class GpuTransformerShard(ModuleShard):
         in0 = data[0] if isinstance(data, tuple) else data
         self.stage.ensure_shape(in0)   # BERT: the sequence length is the input's; output rings are sized after this
         out = self._stage_out(in0.shape[0])
+        if self._static:
+            # captured by the native pipeline: plain launches; a non-final stage that ends on a projection leaves its
+            # last residual add to the link's send kernel
+            res = self.stage.forward(data, out=out, defer_add=not self.shard_config.is_last)
+            self._deferred = self.stage.deferred()
+            return res
         res = self.stage.forward(data, out=out, use_graph=self.use_cuda_graph)
         self._mark_inputs_consumed()
         if self.use_cuda_graph:
             self._slot = (self._slot + 1) % max(1, self.num_slots)
         return res
 
+    # ------------------------------------------------------------------ native pipeline (comm/p2p/_native.py)
+    def _inner(self) -> 'GpuTransformerShard':
+        """The shard that owns the stage (classification shards wrap a model shard)."""
+        return self
+
+    def native_input_spec(self, ubatch: int, dim1: int):
+        """[(shape, dtype)] of the persistent input buffer(s) for micro-batches of `ubatch` items."""
+        stage = self.stage
+        if self.shard_config.is_first:
+            return [self._first_input_spec(ubatch, dim1)]
+        tokens = dim1 or stage.tokens
+        spec = [((ubatch, tokens, stage.inter if stage.first_sub == 3 else stage.hidden), torch.float32)]
+        if stage.in_is_tuple:
+            spec.append(((ubatch, tokens, stage.hidden), torch.float32))
+        return spec
+
+    def _first_input_spec(self, ubatch: int, dim1: int):
+        raise NotImplementedError
+
+    def native_out_bytes(self, max_ubatch: int, max_tokens: int) -> int:
+        """Upper bound of this shard's output payload (fp32 on the wire) for sizing the downstream link's slots."""
+        stage = self.stage
+        if self.shard_config.is_last:
+            n = 1
+            for d in self.native_result_item_shape():
+                n *= d
+            return max_ubatch * n * 4 + 4096
+        widths = {0: 2 * stage.hidden, 2: stage.inter + stage.hidden}.get(stage.last_sub, stage.hidden)
+        return max_ubatch * max_tokens * widths * 4 + 8192
+
+    def native_max_tokens(self) -> int:
+        """Largest sequence length a payload can have."""
+        return self.stage.tokens
+
+    def native_result_item_shape(self):
+        """Per-item shape of the LAST stage's output for this model (known on every rank from the config)."""
+        raise NotImplementedError
+
+    def native_needs_resize(self, ubatch: int, dim1: int) -> bool:
+        return self.stage.needs_resize(ubatch, dim1 or self.stage.tokens)
+
+    def native_forward(self, inputs):
+        """One forward on persistent buffers for graph capture (no hooks, no allocation after the first call per
+        shape): returns [(a, b or None, elements per item)] device addresses of the output payload (a + b)."""
+        inner = self._inner()
+        prev = (self._static, inner._static)
+        self._static = inner._static = True
+        inner._deferred = None
+        try:
+            data = inputs[0] if len(inputs) == 1 else tuple(inputs)
+            out = self.forward(data)
+            outs = out if isinstance(out, tuple) else (out,)
+            ubatch = inputs[0].shape[0]
+            self._native_keep = outs   # the graph writes into these buffers for as long as it lives
+            if inner._deferred is not None and len(outs) == 1:
+                a, b = inner._deferred
+                return [(a, b, outs[0].numel() // ubatch)]
+            for t in outs:
+                if t.dtype != torch.float32 or not t.is_contiguous():
+                    raise RuntimeError("native pipeline: stage outputs must be contiguous fp32 tensors")
+            return [(t.data_ptr(), None, t.numel() // ubatch) for t in outs]
+        finally:
+            self._static, inner._static = prev
+
     # ------------------------------------------------------------------ heads
-    def _cls_rows(self, data: torch.Tensor) -> torch.Tensor:
-        return data[:, 0, :].contiguous()
+    def _cls_rows(self, data: torch.Tensor, dtype=torch.float32, name: str = 'cls_rows') -> torch.Tensor:
+        """Row 0 of every item ([CLS]), gathered (and cast) into a contiguous buffer."""
+        buf = self._tmp(name, (data.shape[0], data.shape[2]), dtype)
+        buf.copy_(data[:, 0, :])
+        return buf
 
     def _classify(self, a16: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
-        return ops.linear(a16, weight, bias, _lib.PE_EPI_F32)
+        out = self._tmp('logits', (a16.shape[0], weight.shape[0]))
+        return ops.linear(a16, weight, bias, _lib.PE_EPI_F32, out=out)

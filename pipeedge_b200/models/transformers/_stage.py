@@ -141,6 +141,11 @@ class EncoderStage:
         self._handle = ctypes.c_void_p()
         self._create()
 
+    def needs_resize(self, ubatch: int, tokens: int) -> bool:
+        """Whether a payload of `ubatch` items of `tokens` tokens would re-create the workspace (which invalidates
+        every CUDA graph captured over it)."""
+        return tokens != self.tokens or ubatch > self.max_ubatch
+
     def ensure_shape(self, in0: torch.Tensor) -> None:
         """Adopt the payload's sequence length / micro-batch (callers must do this BEFORE sizing output buffers)."""
         if in0.shape[1] != self.tokens or in0.shape[0] > self.max_ubatch:
@@ -177,9 +182,18 @@ class EncoderStage:
             return (ubatch, self.tokens, self.inter), skip
         return skip, None
 
+    def deferred(self) -> Optional[Tuple[int, int]]:
+        """Device addresses (a, b) when the last forward left its final residual add to the consumer (output =
+        a + b, see PE_STAGE_DEFER_ADD), else None."""
+        a, b = ctypes.c_void_p(), ctypes.c_void_p()
+        check(LIB.pe_stage_deferred(self._handle, ctypes.byref(a), ctypes.byref(b)))
+        return (a.value, b.value) if a.value else None
+
     def forward(self, data: ShardData, out: Optional[Tuple[torch.Tensor, Optional[torch.Tensor]]] = None,
-                use_graph: bool = False) -> ShardData:
-        """Run the blocks on fp32 CUDA payload(s); `out` supplies persistent output buffers (graph replay)."""
+                use_graph: bool = False, defer_add: bool = False) -> ShardData:
+        """Run the blocks on fp32 CUDA payload(s); `out` supplies persistent output buffers (graph replay).
+        `defer_add` (eager launches only): a stage ending on a projection skips its last residual add - read the two
+        addends with `deferred()` (the link's send kernel adds while it reads)."""
         if self.in_is_tuple:
             in0, in1 = data
         else:
@@ -196,7 +210,8 @@ class EncoderStage:
         out0, out1 = out
         check(LIB.pe_stage_forward(self._handle, in0.data_ptr(), None if in1 is None else in1.data_ptr(),
                                    out0.data_ptr(), None if out1 is None else out1.data_ptr(), ubatch,
-                                   1 if use_graph else 0, torch.cuda.current_stream().cuda_stream))
+                                   1 if use_graph else (_lib.PE_STAGE_DEFER_ADD if defer_add else 0),
+                                   torch.cuda.current_stream().cuda_stream))
         return (out0, out1) if self.out_is_tuple else out0
 
     KERNEL_KINDS = ('cast', 'layernorm', 'gemm_qkv', 'attention', 'gemm_out', 'gemm_fc1', 'gemm_fc2')

@@ -38,7 +38,7 @@ class BertModelShard(GpuTransformerShard):
     def _embed(self, ids: torch.Tensor) -> torch.Tensor:
         batch, seq = ids.shape
         hidden = self.config.hidden_size
-        out = (self._ring('embed', (batch, seq, hidden)) if self.use_cuda_graph else
+        out = (self._ring('embed', (batch, seq, hidden)) if self.persistent else
                torch.empty((batch, seq, hidden), dtype=torch.float32, device=ids.device))
         check(LIB.pe_bert_embed(ids.data_ptr(), self._pos_ids.data_ptr(), self._word.data_ptr(),
                                 self._type0.data_ptr(), self._pos.data_ptr(), self._emb_ln_w.data_ptr(),
@@ -55,9 +55,19 @@ class BertModelShard(GpuTransformerShard):
             data = self._to_device(data)
         data = self._run_blocks(data)
         if self.shard_config.is_last:
-            first16 = self._cls_rows(data).to(torch.float16)
-            data = ops.linear(first16, self._pool_w, self._pool_b, _lib.PE_EPI_TANH_F32)
+            first16 = self._cls_rows(data, torch.float16, 'first16')
+            data = ops.linear(first16, self._pool_w, self._pool_b, _lib.PE_EPI_TANH_F32,
+                              out=self._tmp('pooled', (first16.shape[0], self._pool_w.shape[0])) if self._static else None)
         return data
+
+    def _first_input_spec(self, ubatch: int, dim1: int):
+        return ((ubatch, dim1 or 128), torch.int64)
+
+    def native_max_tokens(self) -> int:
+        return int(self.config.max_position_embeddings)
+
+    def native_result_item_shape(self):
+        return (int(self.config.hidden_size),)
 
     @staticmethod
     def save_weights(model_name: str, model_file: str) -> None:
@@ -83,10 +93,27 @@ class BertShardForSequenceClassification(GpuTransformerShard):
     def forward(self, data: TransformerShardData) -> TransformerShardData:
         """Compute shard layers; on the last stage `classifier(pooled)` (`bert.py:203-209`)."""
         self.bert.use_cuda_graph, self.bert.num_slots = self.use_cuda_graph, self.num_slots
-        data = self.bert(data)
+        data = self.bert.forward(data) if self._static else self.bert(data)
         if self.shard_config.is_last:
-            data = self._classify(data.to(torch.float16), self._cls_w, self._cls_b)
+            if self._static:
+                pooled16 = self._tmp('pooled16', data.shape, torch.float16)
+                pooled16.copy_(data)
+            else:
+                pooled16 = data.to(torch.float16)
+            data = self._classify(pooled16, self._cls_w, self._cls_b)
         return data
+
+    def _inner(self):
+        return self.bert
+
+    def _first_input_spec(self, ubatch: int, dim1: int):
+        return self.bert._first_input_spec(ubatch, dim1)   # pylint: disable=protected-access
+
+    def native_max_tokens(self) -> int:
+        return self.bert.native_max_tokens()
+
+    def native_result_item_shape(self):
+        return (int(self.config.num_labels),)
 
     @staticmethod
     def save_weights(model_name: str, model_file: str) -> None:

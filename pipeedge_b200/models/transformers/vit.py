@@ -58,9 +58,9 @@ class ViTModelShard(GpuTransformerShard):
             raise ValueError(f"expected pixel_values [B,{cfg.num_channels},{cfg.image_size},{cfg.image_size}], "
                              f"got {tuple(pixels.shape)}")
         n_patches = self.tokens - self.N_PREFIX
-        out = (self._ring('embed', (batch, self.tokens, cfg.hidden_size)) if self.use_cuda_graph else
+        out = (self._ring('embed', (batch, self.tokens, cfg.hidden_size)) if self.persistent else
                torch.empty((batch, self.tokens, cfg.hidden_size), dtype=torch.float32, device=pixels.device))
-        work = self._ring('patches', (batch * n_patches, self._kpad), torch.float16) if self.use_cuda_graph else \
+        work = self._ring('patches', (batch * n_patches, self._kpad), torch.float16) if self.persistent else \
             torch.empty((batch * n_patches, self._kpad), dtype=torch.float16, device=pixels.device)
         check(LIB.pe_patch_embed(pixels.data_ptr(), self._conv_w.data_ptr(), self._conv_b.data_ptr(),
                                  self._pos.data_ptr(), self._prefix.data_ptr(), out.data_ptr(), work.data_ptr(), batch,
@@ -77,9 +77,19 @@ class ViTModelShard(GpuTransformerShard):
             # LayerNorm is per token, so the classification shard normalises only the rows it reads
             rows = self._cls_rows(data) if cls_only else data
             f32, f16 = ops.layernorm(rows, self._ln_w, self._ln_b, self.config.layer_norm_eps,
-                                     want_f32=not cls_only, want_f16=cls_only)
+                                     want_f32=not cls_only, want_f16=cls_only,
+                                     out_f32=None if cls_only or not self._static else self._tmp('final_ln', rows.shape),
+                                     out_f16=self._tmp('final_ln16', rows.shape, torch.float16)
+                                     if cls_only and self._static else None)
             data = f16 if cls_only else f32
         return data
+
+    def _first_input_spec(self, ubatch: int, dim1: int):
+        cfg = self.config
+        return ((ubatch, cfg.num_channels, cfg.image_size, cfg.image_size), torch.float32)
+
+    def native_result_item_shape(self):
+        return (self.tokens, self.config.hidden_size)
 
     @torch.no_grad()
     def forward(self, data: TransformerShardData) -> TransformerShardData:
@@ -117,6 +127,15 @@ class ViTShardForImageClassification(GpuTransformerShard):
         if self.shard_config.is_last:
             data = self._classify(data, self._head_w, self._head_b)
         return data
+
+    def _inner(self):
+        return self.vit
+
+    def _first_input_spec(self, ubatch: int, dim1: int):
+        return self.vit._first_input_spec(ubatch, dim1)   # pylint: disable=protected-access
+
+    def native_result_item_shape(self):
+        return (int(self.config.num_labels),)
 
     @staticmethod
     def save_weights(model_name: str, model_file: str, url=None, timeout_sec=None) -> None:

@@ -27,15 +27,22 @@ def _want(t: torch.Tensor, dtype: torch.dtype, name: str) -> None:
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, want_f32: bool = True,
-              want_f16: bool = False) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
-    """LayerNorm over the last dim of an fp32 tensor; returns (f32 or None, f16 or None)."""
+              want_f16: bool = False, out_f32: Optional[torch.Tensor] = None,
+              out_f16: Optional[torch.Tensor] = None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """LayerNorm over the last dim of an fp32 tensor; returns (f32 or None, f16 or None). `out_f32` / `out_f16`
+    supply persistent output buffers (CUDA-graph capture)."""
     _want(x, torch.float32, 'x')
     _want(gamma, torch.float32, 'gamma')
     _want(beta, torch.float32, 'beta')
     hidden = x.shape[-1]
     rows = x.numel() // hidden
-    o32 = torch.empty_like(x) if want_f32 else None
-    o16 = torch.empty(x.shape, dtype=torch.float16, device=x.device) if want_f16 else None
+    o32 = (out_f32 if out_f32 is not None else torch.empty_like(x)) if want_f32 else None
+    o16 = (out_f16 if out_f16 is not None else torch.empty(x.shape, dtype=torch.float16, device=x.device)) \
+        if want_f16 else None
+    if o32 is not None:
+        _want(o32, torch.float32, 'out_f32')
+    if o16 is not None:
+        _want(o16, torch.float16, 'out_f16')
     check(LIB.pe_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), float(eps), _ptr(o32), _ptr(o16), rows,
                            hidden, _stream()))
     return o32, o16

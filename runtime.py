@@ -128,6 +128,14 @@ def forward_pre_hook_quant_decode(_module, input_arg: Tuple[Tuple[torch.Tensor, 
     return (tuple(forward_tensor),)         # a (data, skip) tuple payload
 
 
+# What the native pipeline (pipeedge_b200/comm/p2p/_native.py) does with each hook: the quantisation pair is performed by
+# the links' send / receive kernels (same codes, same decoded values), the monitor pair is a no-op unless MONITORING=1.
+forward_hook_quant_encode._pe_native = True                 # pylint: disable=protected-access
+forward_pre_hook_quant_decode._pe_native = True             # pylint: disable=protected-access
+forward_pre_hook_monitor._pe_native = lambda: _device_iters is None    # pylint: disable=protected-access
+forward_hook_monitor._pe_native = lambda: _device_iters is None        # pylint: disable=protected-access
+
+
 def _payload_tensors(outputs) -> Tuple[torch.Tensor, ...]:
     return (outputs,) if isinstance(outputs, torch.Tensor) else tuple(outputs)
 

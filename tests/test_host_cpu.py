@@ -21,7 +21,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == set(_lib.SYMBOLS), (declared ^ set(_lib.SYMBOLS))
     for name in declared:
         assert hasattr(_lib.LIB, name), name
-    assert _lib.LIB.pe_abi_version() == 1
+    assert _lib.LIB.pe_abi_version() == _lib.PE_ABI_VERSION == 2
     assert _lib.LIB.pe_quant_words(152064, 8) == 38016     # C5 hop: 4.87 MB of codes per 32 items
     assert _lib.LIB.pe_quant_words(10, 6) == 2              # 5 codes per word
     assert _lib.LIB.pe_quant_words(10, 0) == 0
