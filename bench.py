@@ -10,15 +10,23 @@ A STEP is one micro-batch through the whole pipeline (BASELINE.json: images/s or
 Default workload = BASELINE.json configs[1]'s model and micro-batch (google/vit-base-patch16-224, ubatch 8,
 fp16 operands / fp32 accumulate) with the 48 sub-layers split evenly over the N stages ([1,24,25,48] at N=2).
 
+Every N runs the same code: DistP2pContext (N > 1) + DistP2pPipelineStage on the native pipeline (one CUDA graph per
+stage micro-batch, peer-memory links between the GPUs, `pipeedge_b200/comm/p2p/_native.py`); graphs are captured before
+the warm-up, so the first timed micro-batch is already a replay.
+
 One JSON line is printed by rank 0:
-  value        whole-pipeline throughput with inputs already resident in HBM (CUDA-event timed, max over ranks)
+  value        whole-pipeline throughput with inputs already resident in HBM: device time (CUDA events) from the first
+               graph launch to the last micro-batch leaving each rank / the last result reaching the data rank, max
+               over ranks
   e2e          the same through the public API with pinned HOST inputs: H2D of every micro-batch and D2H of
-               every result inside the timed region
-  roofline     the dominant kernel (the FC1 tcgen05 GEMM): algorithmic FLOPs per launch / its CUDA-event
-               duration inside a live forward, against MEASURED_PEAKS.json
-  cpu_baseline the CPU oracle port (oracle/shards.py, torch fp32 on all host cores) on a bounded sample
-`--impl reference` times that CPU port as the reference arm (the reference is Python and cannot travel to
-the GPU box).
+               every result inside the (wall-clock, device-synchronised) timed region
+  checksum     sum |logits| over the first 16 results: identical inputs at every N, so it must not depend on N
+  roofline     N = 1: the dominant kernel (the FC1 tcgen05 GEMM): algorithmic FLOPs per launch / its CUDA-event
+               duration, against MEASURED_PEAKS.json; N > 1: the bottleneck STAGE (its GEMM + attention FLOPs over its
+               event-timed kernel sequence), per-rank breakdown under `stages`
+  cpu_baseline the CPU oracle port (oracle/shards.py, torch fp32 on the host cores) on a bounded sample
+`--impl reference` times that CPU port as the reference arm with the same thread calibration and the same `config`
+(the reference is Python and cannot travel to the GPU box).
 """
 import argparse
 import faulthandler
@@ -43,6 +51,7 @@ WORKLOADS = {
     'vit-large': ('google/vit-large-patch16-224', 16, 0, 0, 'images/sec per pipeline', 'images/s'),
     'bert-base': ('textattack/bert-base-uncased-CoLA', 32, 128, 0, 'sequences/sec per pipeline', 'sequences/s'),
     'deit-base-q8': ('facebook/deit-base-distilled-patch16-224', 32, 0, 8, 'images/sec per pipeline', 'images/s'),
+    'vit-base-b1': ('google/vit-base-patch16-224', 1, 0, 0, 'images/sec per pipeline', 'images/s'),   # BASELINE configs[0]
 }
 N_INPUTS = 16   # distinct resident micro-batches the timed loop rotates over
 
@@ -122,7 +131,7 @@ def load_peaks() -> dict:
 
 
 # ---------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port, timed (cpu_baseline and --impl reference)
+# CPU arm: the oracle port, timed (cpu_baseline and --impl reference share every line of this)
 # ---------------------------------------------------------------------------------------------------
 def usable_cores() -> int:
     """Host threads this process may really use: affinity mask, capped by a cgroup CPU quota if one is set."""
@@ -141,70 +150,77 @@ def usable_cores() -> int:
 
 
 def cpu_forward_timer(spec, ubatch: int, seq: int):
-    """Returns (callable running one micro-batch through the whole model on the CPU, threads used).
+    """Returns (callable running one micro-batch through the whole model on the CPU, threads used, calibration log).
 
-    "All the host threads it can use": the thread count is calibrated on one encoder block over
-    {8, 16, 32, 64, all usable} - on a many-core shared box torch's fp32 GEMMs get SLOWER past a point."""
+    "All the host threads it can use": on a many-core shared box torch's fp32 GEMMs get SLOWER past a point, so the
+    thread count is calibrated - median of 3 repetitions per candidate of the FULL model (of its first two blocks when
+    a full forward takes more than 0.6 s), candidates {8, 16, 32, 64, 96, all usable}."""
     from oracle import shards as osh   # the one place bench.py may execute oracle/ (as the timed CPU baseline)
     weights = synth_weights(spec, seed=0)
     model = osh.PreparedShard(spec, weights, 1, spec.layers)
     x = synth_input(spec, ubatch, seed=1, seq_len=seq or 128)
     limit = usable_cores()
-    block = osh.PreparedShard(spec, weights, 1, 4)
-    best, best_t = 1, float('inf')
-    for n in sorted({min(c, limit) for c in (8, 16, 32, 64, limit)}):
+    torch.set_num_threads(min(16, limit))
+    model.forward(x)                      # warm-up: thread pool, oneDNN primitive caches
+    t0 = time.perf_counter()
+    model.forward(x)
+    probe = model if time.perf_counter() - t0 < 0.6 else osh.PreparedShard(spec, weights, 1, 8)
+    log = {}
+    for n in sorted({min(c, limit) for c in (8, 16, 32, 64, 96, limit)}):
         torch.set_num_threads(n)
-        block.forward(x)
-        t0 = time.perf_counter()
-        block.forward(x)
-        dt = time.perf_counter() - t0
-        if dt < best_t:
-            best, best_t = n, dt
+        probe.forward(x)
+        reps = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            probe.forward(x)
+            reps.append(time.perf_counter() - t0)
+        log[n] = statistics.median(reps)
+    best = min(log, key=log.get)
     torch.set_num_threads(best)
-    return (lambda: model.forward(x)), best
+    return (lambda: model.forward(x)), best, {'host_cores': limit, 'probe': 'full model' if probe is model else '2 blocks',
+                                              'median_s_by_threads': {str(k): round(v, 4) for k, v in log.items()}}
 
 
-def cpu_baseline(spec, ubatch: int, seq: int, unit: str, budget_s: float = 15.0) -> dict:
-    fwd, cores = cpu_forward_timer(spec, ubatch, seq)
-    fwd()   # warm-up (thread pool, oneDNN primitive caches)
+def cpu_sample(spec, ubatch: int, seq: int, unit: str, max_steps: int, budget_s: float) -> dict:
+    """Time the CPU port on a bounded sample; the same routine serves `cpu_baseline` and `--impl reference`."""
+    fwd, cores, cal = cpu_forward_timer(spec, ubatch, seq)
+    fwd()
     t0 = time.perf_counter()
     n = 0
-    while n < 2 or (time.perf_counter() - t0 < budget_s and n < 64):
+    while n < 2 or (n < max_steps and time.perf_counter() - t0 < budget_s):
         fwd()
         n += 1
     dt = time.perf_counter() - t0
-    return {'value': n * ubatch / dt, 'unit': unit, 'cores': cores, 'kind': 'port',
+    return {'value': n * ubatch / dt, 'unit': unit, 'cores': cores, 'kind': 'port', 'steps': n, 'seconds': dt,
+            'calibration': cal,
             'sample': f"{n} micro-batches of {ubatch} through all {spec.layers} sub-layers, torch fp32 CPU "
-                      f"({dt:.1f} s), 1 process x {cores} threads (best of a thread-count calibration)"}
+                      f"({dt:.1f} s), 1 process x {cores} threads of {cal['host_cores']} usable host cores "
+                      "(median-of-3 thread calibration)"}
 
 
-def run_reference_arm(args, spec, ubatch, seq, metric, unit, workload):
+def make_config(workload, spec, ubatch, seq_eff, parts, qbit, world) -> dict:
+    """The `config` object: identical for both arms."""
+    return {'workload': workload, 'model': spec.name, 'ubatch': ubatch, 'seq_len': seq_eff,
+            'partition': [list(p) for p in parts], 'quant': [qbit] * (world - 1) + [0], 'n_stages': world,
+            'inputs': f"{N_INPUTS} distinct synthetic micro-batches rotated (seeds 100..{100 + N_INPUTS - 1}); weights seed 0"}
+
+
+def run_reference_arm(args, spec, ubatch, seq, qbit, metric, unit, workload):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
-        return   # the CPU arm is a single process using every host core; other ranks have no work
-    fwd, cores = cpu_forward_timer(spec, ubatch, seq)
-    steps = max(1, args.steps)
-    for _ in range(max(1, min(args.warmup, 2))):
-        fwd()
-    t0 = time.perf_counter()
-    done = 0
-    for _ in range(steps):   # bounded so the whole arm ends within a few minutes
-        fwd()
-        done += 1
-        if time.perf_counter() - t0 > 120:
-            break
-    dt = time.perf_counter() - t0
-    value = done * ubatch / dt
-    sample = f"{done} micro-batches of {ubatch} (of {steps} requested), torch fp32 CPU, {cores} threads"
+        return   # the CPU arm is a single process using the host cores; other ranks have no work
+    world = int(os.environ.get('WORLD_SIZE', str(args.gpus)))
+    res = cpu_sample(spec, ubatch, seq, unit, max_steps=max(2, args.steps), budget_s=120.0)
     print(json.dumps({
-        'impl': 'reference', 'metric': metric, 'value': value, 'unit': unit, 'n_gpus': args.gpus, 'steps': done,
-        'warmup': args.warmup, 'ms_per_step': dt / done * 1e3, 'higher_is_better': True, 'scaling': 'strong',
-        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': workload, 'model': spec.name, 'ubatch': ubatch, 'seq_len': seq or spec.tokens,
-                   'note': "CPU port of the reference path (oracle/shards.py); the reference package is Python and "
-                           "cannot travel to the GPU box"},
-        'cpu_baseline': {'value': value, 'unit': unit, 'cores': cores, 'kind': 'port', 'sample': sample},
-        'e2e': {'value': value, 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'impl': 'reference', 'metric': metric, 'value': res['value'], 'unit': unit, 'n_gpus': args.gpus,
+        'steps': res['steps'], 'warmup': args.warmup, 'ms_per_step': res['seconds'] / res['steps'] * 1e3,
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': make_config(workload, spec, ubatch, seq or spec.tokens, even_partition(spec.layers, max(1, world)),
+                              qbit, max(1, world)),
+        'note': "CPU port of the reference path (oracle/shards.py) in ONE process on the host cores; the reference "
+                "package is Python and cannot travel to the GPU box, and its N-rank Gloo pipeline is not what is timed",
+        'cpu_baseline': {k: res[k] for k in ('value', 'unit', 'cores', 'kind', 'sample', 'calibration')},
+        'e2e': {'value': res['value'], 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }))
 
 
@@ -300,273 +316,247 @@ def roofline_from_profile(shard, sample, spec, ubatch, seq, peaks, step_ms=None)
             'breakdown': breakdown, 'eager_forward_ms': total_ms}
 
 
-def run_single_gpu(args, spec, ubatch, seq, qbit, metric, unit, workload):
-    from pipeedge_b200 import ops
-    from pipeedge_b200.comm.p2p import DistP2pPipelineStage
-    torch.cuda.set_device(0)
-    dev = torch.device('cuda', 0)
-    weights = synth_weights(spec, seed=0)
-    shard = make_shard(spec, weights, 1, spec.layers)
-    shard.use_cuda_graph = True
-    del weights
-    seq_eff = seq or spec.tokens
-    inputs_host = [synth_input(spec, ubatch, seed=100 + i, seq_len=seq or 128).pin_memory() for i in range(N_INPUTS)]
-    inputs_dev = [x.to(dev) for x in inputs_host]
-    steps, warmup = args.steps, max(3, args.warmup)
-    stream = torch.cuda.Stream(device=dev)
-    results = [None] * 4
-
-    # ---- value: inputs resident in HBM, CUDA-event timed
-    with torch.cuda.stream(stream):
-        for i in range(warmup):
-            results[i % 4] = shard(inputs_dev[i % N_INPUTS])
-        stream.synchronize()
-        launches0 = ops.launch_count()
-        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(0) as clocks:
-            torch.cuda.synchronize()
-            start.record(stream)
-            for i in range(steps):
-                results[i % 4] = shard(inputs_dev[i % N_INPUTS])
-            end.record(stream)
-            torch.cuda.synchronize()
-        ms = start.elapsed_time(end)
-        launches = ops.launch_count() - launches0
-        logits_check = results[(steps - 1) % 4].float().abs().sum().item()
-    value = steps * ubatch / (ms * 1e-3)
-    if args.quick:
-        print(json.dumps({'metric': metric, 'value': value, 'unit': unit, 'n_gpus': 1, 'steps': steps,
-                          'ms_per_step': ms / steps, 'gpu_launches': int(launches), 'quick': True}))
-        return
-
-    # ---- e2e: public API (DistP2pPipelineStage threads), pinned host inputs, D2H of every result
-    done = threading.Event()
-    got = []
-    target = [0]
-
-    def results_cb(t):
-        got.append(t.cpu())        # D2H read of the step's result (logits)
-        if len(got) >= target[0]:
-            done.set()
-
-    shard_e2e = shard
-    with DistP2pPipelineStage(None, None, shard_e2e, results_cb) as stage_ctx:
-        target[0] = warmup
-        for i in range(warmup):
-            stage_ctx.enqueue_tensor(inputs_host[i % N_INPUTS])
-        assert done.wait(300), "e2e warm-up did not finish"
-        stage_ctx.check_workers()
-        got.clear()
-        done.clear()
-        target[0] = steps
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for i in range(steps):
-            stage_ctx.enqueue_tensor(inputs_host[i % N_INPUTS])
-        assert done.wait(600), "e2e run did not finish"
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
-        stage_ctx.check_workers()
-    h2d = inputs_host[0].numel() * inputs_host[0].element_size()
-    d2h = got[0].numel() * got[0].element_size()
-    e2e = {'value': steps * ubatch / e2e_s, 'unit': unit, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-           'ms_per_step': e2e_s / steps * 1e3}
-
-    # ---- roofline of the dominant kernel (graph of back-to-back launches) + per-kernel shares (event-bracketed forwards)
-    peaks = load_peaks()
-    with torch.cuda.stream(stream):
-        emb = shard.vit._embed(inputs_dev[0]) if spec.family != 'bert' else shard.bert._embed(inputs_dev[0])  # noqa
-        roof = roofline_from_profile(shard, emb, spec, ubatch, seq_eff, peaks, step_ms=ms / steps)
-    total_flops = flops_per_item(spec, seq_eff)
-
-    out = {
-        'metric': metric, 'value': value, 'unit': unit, 'n_gpus': 1, 'steps': steps, 'warmup': warmup,
-        'ms_per_step': ms / steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-        'dtype': 'f16', 'data': 'synthetic',
-        'config': {'workload': workload, 'model': spec.name, 'ubatch': ubatch, 'seq_len': seq_eff,
-                   'partition': [1, spec.layers], 'quant': qbit, 'cuda_graph': True,
-                   'l2': f"timed loop rotates over {N_INPUTS} distinct resident micro-batches; fp16 weights of the "
-                         f"stage ({spec.blocks * (4 * spec.hidden ** 2 + 2 * spec.hidden * spec.inter) * 2 / 1e6:.0f} MB) "
-                         "exceed the 126 MB L2 and stream from HBM every step"},
-        'clocks': clocks.summary(), 'e2e': e2e, 'gpu_launches': int(launches),
-        'roofline': roof,
-        'model_tflops': value * total_flops / 1e12,
-        'model_frac_of_sustained_peak': value * total_flops / 1e12 / peaks['bf16_tflops_sustained'],
-        'checksum': logits_check,
-    }
-    if not args.no_cpu_baseline:
-        out['cpu_baseline'] = cpu_baseline(spec, ubatch, seq, unit)
-    print(json.dumps(out))
+def stage_roofline(shard, spec, ubatch, seq, parts_rank, dev) -> dict:
+    """This rank's stage, kernel by kernel (CUDA events around every launch of eager forwards: upper bounds, launch
+    overlap is lost): GEMM + attention FLOPs of its sub-layers over the sum of its kernel times."""
+    stage = shard.stage
+    lo, hi = parts_rank
+    if stage.in_is_tuple:
+        width = stage.inter if stage.first_sub == 3 else stage.hidden
+        sample = (torch.randn(ubatch, seq, width, device=dev), torch.randn(ubatch, seq, stage.hidden, device=dev))
+    else:
+        sample = torch.randn(ubatch, seq, stage.hidden, device=dev)
+    acc = {}
+    reps = 3
+    for _ in range(reps):
+        for kind, ms in stage.profile(sample):
+            acc[kind] = acc.get(kind, 0.0) + ms
+    m, h, i = ubatch * seq, spec.hidden, spec.inter
+    per_sub = {0: 2.0 * m * 3 * h * h + 4.0 * ubatch * seq * seq * h, 1: 2.0 * m * h * h, 2: 2.0 * m * i * h,
+               3: 2.0 * m * h * i}
+    flops = sum(per_sub[(layer - 1) % 4] for layer in range(lo, hi + 1))
+    total_ms = sum(acc.values()) / reps
+    return {'layers': [lo, hi], 'flops': flops, 'eager_ms': total_ms, 'tflops': flops / (total_ms * 1e-3) / 1e12,
+            'kernel_ms': {k: round(v / reps, 4) for k, v in acc.items()}}
 
 
-def run_pipeline(args, spec, ubatch, seq, qbit, metric, unit, workload):
-    """N > 1: one stage per rank through DistP2pContext / DistP2pPipelineStage (the runtime.py path)."""
+def run_gpu(args, spec, ubatch, seq, qbit, metric, unit, workload):
+    """All N: one stage per rank through DistP2pContext / DistP2pPipelineStage (the runtime.py path)."""
+    import contextlib
     import torch.distributed as dist
-    # hand-off queues three deep (the reference's are one deep): more micro-batches in flight hide the host-side
-    # hand-offs between the per-stage threads; results are unchanged (tests/test_pipeline_gpu.py)
-    os.environ.setdefault('PIPEEDGE_QUEUE_DEPTH', '3')
-    from pipeedge_b200 import ops
-    from pipeedge_b200.comm.p2p import DistP2pContext, DistP2pPipelineStage, queue_depth
+    from pipeedge_b200.comm.p2p import DistP2pContext, DistP2pPipelineStage
     import runtime as rt
-    rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
-    local = int(os.environ.get('LOCAL_RANK', rank))
+    rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', rank)) % torch.cuda.device_count()
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    os.environ.setdefault('PIPEEDGE_MAX_UBATCH', str(max(ubatch, 8)))
     parts = even_partition(spec.layers, world)
     weights = synth_weights(spec, seed=0)
     shard = make_shard(spec, weights, *parts[rank])
-    shard.use_cuda_graph = True
     del weights
     steps, warmup = args.steps, max(3, args.warmup)
     seq_eff = seq or spec.tokens
+    dim1 = seq_eff if spec.family == 'bert' else 0
     last = world - 1
+    # the same module hooks runtime.py installs; the native pipeline performs them inside its link kernels
     shard.register_buffer('quant_bit', torch.tensor(qbit if rank != last else 0), persistent=False)
     if rank != last:
         shard.register_forward_hook(rt.forward_hook_quant_encode)
     if rank != 0:
         shard.register_forward_pre_hook(rt.forward_pre_hook_quant_decode)
 
-    counter = {'n': 0, 'start': None, 'end': None, 'launch0': 0, 'launch1': 0}
-    phase_done = threading.Event()
-    phase = {'target': 0, 'timed': False}
-
-    def work(payload):
-        if phase['timed'] and counter['n'] == 0:
-            counter['start'] = torch.cuda.Event(enable_timing=True)
-            counter['start'].record()
-            counter['launch0'] = ops.launch_count()
-        out = shard(payload)
-        counter['n'] += 1
-        if counter['n'] == phase['target']:
-            if phase['timed']:
-                counter['end'] = torch.cuda.Event(enable_timing=True)
-                counter['end'].record()
-                counter['launch1'] = ops.launch_count()
-            if rank != 0:
-                phase_done.set()
-        return out
-
     got = []
     res_done = threading.Event()
-    e2e_mode = {'on': False}
+    target = {'n': 0}
 
     def results_cb(t):
-        got.append(t.cpu() if e2e_mode['on'] else t)
-        if len(got) >= phase['target']:
+        got.append(t)
+        if len(got) >= target['n']:
             res_done.set()
 
+    phase_q = []
+    phase_evt = threading.Event()
     stop = threading.Event()
-    go = threading.Event()
 
     def handle_cmd(cmd, tensors):
         if cmd == 0:
             stop.set()
-        elif cmd == 2:   # next phase: [target, timed]
-            phase['target'], phase['timed'] = int(tensors[0][0]), bool(tensors[0][1])
-            counter['n'] = 0
-            go.set()
+        elif cmd == 2:     # phase boundary: [kind]
+            phase_q.append(int(tensors[0][0]))
+            phase_evt.set()
 
-    def gather_max(x: float) -> float:
+    def wait_cmd():
+        assert phase_evt.wait(900), "no phase command from rank 0"
+        kind = phase_q.pop(0)
+        if not phase_q:
+            phase_evt.clear()
+        return kind
+
+    def allmax(x: float) -> float:
+        if world == 1:
+            return x
         t = torch.tensor([x], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0])
 
-    def gather_sum(x: float) -> float:
+    def allsum(x: float) -> float:
+        if world == 1:
+            return x
         t = torch.tensor([x], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t[0])
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
     out = None
-    with DistP2pContext(('gloo',), {'world_size': world, 'rank': rank}, handle_cmd) as ctx:
-        src = last if rank == 0 else rank - 1
-        dst = 0 if rank == last else rank + 1
-        with DistP2pPipelineStage(src, dst, work, results_cb if rank == 0 else None) as stage_ctx:
+    ctx_mgr = DistP2pContext(('gloo',), {'world_size': world, 'rank': rank}, handle_cmd) if world > 1 \
+        else contextlib.nullcontext()
+    with ctx_mgr as ctx:
+        src = None if world == 1 else (last if rank == 0 else rank - 1)
+        dst = None if world == 1 else (0 if rank == last else rank + 1)
+        with DistP2pPipelineStage(src, dst, shard, results_cb if rank == 0 else None) as stage_ctx:
+            native = stage_ctx.native
+            if native is None:
+                raise SystemExit("bench.py: the native pipeline was not selected (PIPEEDGE_NATIVE=0 or a rank without a "
+                                 "B200 shard?)")
+            stage_ctx.prepare(ubatch, dim1)          # graph capture happens here, before any timed or warm-up step
             inputs_host = inputs_dev = None
             if rank == 0:
                 inputs_host = [synth_input(spec, ubatch, seed=100 + i, seq_len=seq or 128).pin_memory()
                                for i in range(N_INPUTS)]
                 inputs_dev = [x.to(dev) for x in inputs_host]
+            torch.cuda.synchronize()
+            barrier()
 
-            def run_phase(n, timed, host):
-                """Rank 0 drives: announce the phase, feed n micro-batches, wait for the n results."""
-                dist.barrier()
-                if rank == 0:
-                    phase['target'], phase['timed'] = n, timed
-                    counter['n'] = 0
-                    ctx.cmd_broadcast(2, (torch.tensor([n, int(timed)]),))
-                else:
-                    assert go.wait(600)
-                    go.clear()
-                dist.barrier()
+            def run_phase(n, host):
+                """Rank 0 feeds n micro-batches and collects n results; every rank times its device window."""
+                native.timing_reset()
+                barrier()
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
                 if rank == 0:
                     got.clear()
                     res_done.clear()
-                    e2e_mode['on'] = host
+                    target['n'] = n
                     src_list = inputs_host if host else inputs_dev
                     for i in range(n):
                         stage_ctx.enqueue_tensor(src_list[i % N_INPUTS])
                     assert res_done.wait(900), "pipeline results did not arrive"
+                    native.sync()
+                    torch.cuda.synchronize()
+                    wall = time.perf_counter() - t0
+                    if world > 1:
+                        ctx.cmd_broadcast(2, (torch.tensor([1]),))     # every result is back: the phase is over
                 else:
-                    assert phase_done.wait(900), "stage did not finish its micro-batches"
-                    phase_done.clear()
-                torch.cuda.synchronize()
-                wall = time.perf_counter() - t0
+                    wait_cmd()
+                    native.sync()
+                    wall = time.perf_counter() - t0
                 stage_ctx.check_workers()
-                dist.barrier()
-                return wall
+                tim = native.timing()
+                barrier()
+                return wall, tim
 
-            run_phase(warmup, False, False)
-            stats0 = stage_ctx.stats()
+            run_phase(warmup, False)
             with ClockSampler(local) as clocks:
-                run_phase(steps, True, False)
-            stats1 = stage_ctx.stats()
-            dev_ms = counter['start'].elapsed_time(counter['end'])
-            ms = gather_max(dev_ms)
-            launches = gather_sum(counter['launch1'] - counter['launch0'])
-            # host time per micro-batch and stage thread inside the timed phase (busy = running Python / enqueuing,
-            # wait = blocked on its queue or socket): shows which rank's host loop bounds the pipeline
-            mine = {name: {k: round((stats1[name][k] - stats0[name][k]) / steps * 1e6, 1) for k in ('busy_s', 'wait_s')}
-                    for name in stats1 if name in stats0}
-            host_stats = [None] * world
-            dist.all_gather_object(host_stats, mine)
-            run_phase(warmup, False, True)
-            e2e_wall = gather_max(run_phase(steps, False, True))
+                _, tim = run_phase(steps, False)
+            ms_rank = max(tim['compute_ms'], tim['results_ms'])
+            ms = allmax(ms_rank)
+            kernels = allsum(float(tim['kernels'])) + steps     # + the data rank's results-get kernel per micro-batch
+            checksum = None
+            if rank == 0:
+                checksum = float(sum(t.double().abs().sum() for t in got[:N_INPUTS]))
+            run_phase(warmup, True)
+            e2e_wall, _ = run_phase(steps, True)
+            e2e_wall = allmax(e2e_wall) if world > 1 else e2e_wall
+            e2e_checksum = float(sum(t.double().abs().sum() for t in got[:N_INPUTS])) if rank == 0 else None
+            # per-stage kernel roofline (eager, event-bracketed) after the timed phases
+            with torch.cuda.stream(torch.cuda.Stream(device=dev)):
+                mine = stage_roofline(shard, spec, ubatch, seq_eff, parts[rank], dev)
+                torch.cuda.current_stream().synchronize()
+            stages = [mine]
+            if world > 1:
+                stages = [None] * world
+                dist.all_gather_object(stages, mine)
             if rank == 0:
                 peaks = load_peaks()
                 value = steps * ubatch / (ms * 1e-3)
                 total_flops = flops_per_item(spec, seq_eff)
                 h2d = inputs_host[0].numel() * inputs_host[0].element_size()
                 d2h = got[0].numel() * got[0].element_size()
+                cfg = make_config(workload, spec, ubatch, seq_eff, parts, qbit, world)
+                hop_bytes = ubatch * seq_eff * spec.hidden * (1 if qbit == 8 else 4) if world > 1 else 0
                 out = {
                     'metric': metric, 'value': value, 'unit': unit, 'n_gpus': world, 'steps': steps, 'warmup': warmup,
                     'ms_per_step': ms / steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-                    'dtype': 'f16', 'data': 'synthetic',
-                    'config': {'workload': workload, 'model': spec.name, 'ubatch': ubatch, 'seq_len': seq_eff,
-                               'partition': [list(p) for p in parts], 'quant': qbit, 'cuda_graph': True,
-                               'queue_depth': queue_depth(),
-                               'hop': 'NCCL P2P per-direction communicators, fp32 activations'
-                                      + (f' quantised to {qbit} bits' if qbit else ''),
-                               'l2': f"timed loop rotates over {N_INPUTS} distinct resident micro-batches; per-stage "
-                                     "weights may be L2-resident, as in steady-state serving"},
+                    'dtype': 'f16', 'data': 'synthetic', 'config': cfg,
+                    'pipeline': {'impl': 'native: one CUDA graph per stage micro-batch, peer-memory links (cudaIpc rings, '
+                                         'device-polled flags)' + (f', {qbit}-bit QuantPipe fused into the send kernel' if qbit else ''),
+                                 'graph_kernels_per_microbatch': native.graph_kernels.get((ubatch, dim1)),
+                                 'hop_bytes_per_microbatch': hop_bytes,
+                                 'l2': f"timed loop rotates over {N_INPUTS} distinct resident micro-batches"
+                                       + ("; the stage's fp16 weights "
+                                          f"({spec.blocks * (4 * spec.hidden ** 2 + 2 * spec.hidden * spec.inter) * 2 / 1e6:.0f} MB) "
+                                          "exceed the 126 MB L2 and stream from HBM every step" if world == 1 else
+                                          "; per-stage weights may be L2-resident, as in steady-state serving")},
                     'clocks': clocks.summary(),
                     'e2e': {'value': steps * ubatch / e2e_wall, 'unit': unit, 'h2d_bytes_per_step': h2d,
                             'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_wall / steps * 1e3},
-                    'gpu_launches': int(launches),
-                    'host_us_per_step': {f'rank{r}': st for r, st in enumerate(host_stats)},
-                    'roofline': {'bound': 'tensor', 'kernel': 'stage GEMMs (tcgen05), pipeline aggregate',
-                                 'achieved': value * total_flops / 1e12 / world,
-                                 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-                                 'frac': value * total_flops / 1e12 / world / peaks['bf16_tflops_sustained'],
-                                 'traffic': None, 'note': 'per-GPU model FLOP rate; per-kernel roofline is in the N=1 line'},
+                    'gpu_launches': int(kernels),
+                    'checksum': checksum, 'checksum_e2e': e2e_checksum,
+                    'model_tflops': value * total_flops / 1e12,
+                    'model_frac_of_sustained_peak_per_gpu': value * total_flops / 1e12 / world / peaks['bf16_tflops_sustained'],
+                    'stages': stages,
                 }
-            if rank == 0:
+                if world == 1:
+                    with torch.cuda.stream(torch.cuda.Stream(device=dev)):
+                        inner = shard.vit if spec.family != 'bert' else shard.bert
+                        emb = inner._embed(inputs_dev[0])   # noqa: protected access - the stage's input
+                        out['roofline'] = roofline_from_profile(shard, emb, spec, ubatch, seq_eff, peaks, step_ms=ms / steps)
+                else:
+                    worst = max(stages, key=lambda st: st['eager_ms'])
+                    out['roofline'] = {'bound': 'tensor', 'kernel': f"bottleneck stage {worst['layers']} (tcgen05 GEMMs + attention)",
+                                       'achieved': worst['tflops'], 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
+                                       'frac': worst['tflops'] / peaks['bf16_tflops_sustained'], 'traffic': None,
+                                       'note': 'stage FLOPs / sum of its event-bracketed kernel times (upper bound on time); the '
+                                               'per-kernel roofline is in the N=1 line',
+                                       'pipeline_frac_of_stage_bound': (ms / steps) / worst['eager_ms']}
+            if rank == 0 and world > 1:
                 ctx.cmd_broadcast(0)
-            else:
+            elif world > 1:
                 stop.wait(60)
     if rank == 0 and out is not None:
+        if not args.no_cpu_baseline and world == 1:
+            res = cpu_sample(spec, ubatch, seq, unit, max_steps=64, budget_s=15.0)
+            out['cpu_baseline'] = {k: res[k] for k in ('value', 'unit', 'cores', 'kind', 'sample', 'calibration')}
         print(json.dumps(out))
+
+
+def run_quick(args, spec, ubatch, seq):
+    """`--quick`: a bare resident-input loop of direct shard calls on one GPU (for ncu runs)."""
+    from pipeedge_b200 import ops
+    torch.cuda.set_device(0)
+    dev = torch.device('cuda', 0)
+    shard = make_shard(spec, synth_weights(spec, seed=0), 1, spec.layers)
+    shard.use_cuda_graph = not args.eager
+    xs = [synth_input(spec, ubatch, seed=100 + i, seq_len=seq or 128).to(dev) for i in range(4)]
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        for i in range(max(3, args.warmup)):
+            shard(xs[i % 4])
+        stream.synchronize()
+        l0 = ops.launch_count()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record(stream)
+        for i in range(args.steps):
+            shard(xs[i % 4])
+        end.record(stream)
+        torch.cuda.synchronize()
+    ms = start.elapsed_time(end)
+    print(json.dumps({'quick': True, 'value': args.steps * ubatch / (ms * 1e-3), 'ms_per_step': ms / args.steps,
+                      'gpu_launches': int(ops.launch_count() - l0)}))
 
 
 def main():
@@ -579,7 +569,8 @@ def main():
     ap.add_argument('--workload', choices=sorted(WORKLOADS), default='vit-base')
     ap.add_argument('--ubatch', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--quick', action='store_true', help='only the resident-input timed loop (for ncu runs)')
+    ap.add_argument('--quick', action='store_true', help='only a resident-input loop of direct shard calls (for ncu runs)')
+    ap.add_argument('--eager', action='store_true', help='with --quick: no CUDA graph (every kernel visible to ncu)')
     args = ap.parse_args()
     model, ubatch, seq, qbit, metric, unit = WORKLOADS[args.workload]
     ubatch = args.ubatch or ubatch
@@ -587,21 +578,16 @@ def main():
     if args.impl == 'reference':
         if args.steps == 300:
             args.steps = 24   # a bounded CPU sample by default
-        run_reference_arm(args, spec, ubatch, seq, metric, unit, args.workload)
+        run_reference_arm(args, spec, ubatch, seq, qbit, metric, unit, args.workload)
         return
-    world = int(os.environ.get('WORLD_SIZE', '1'))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - pipeedge_b200 has no CPU fallback (use --impl reference for the CPU arm)")
-    if world > 1:
-        run_pipeline(args, spec, ubatch, seq, qbit, metric, unit, args.workload)
-        # Every hop, thread and process group is shut down by now. Leave without the interpreter's and the CUDA / NCCL
-        # libraries' exit-time teardown: with 4 ranks one of them regularly died with SIGSEGV inside it (after
-        # Py_Finalize: faulthandler was already off), which torchrun reports as a failed job.
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
-    else:
-        run_single_gpu(args, spec, ubatch, seq, qbit, metric, unit, args.workload)
+    if args.quick:
+        run_quick(args, spec, ubatch, seq)
+        return
+    run_gpu(args, spec, ubatch, seq, qbit, metric, unit, args.workload)
+    sys.stdout.flush()
+    sys.stderr.flush()
 
 
 if __name__ == '__main__':

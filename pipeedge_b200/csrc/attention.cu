@@ -9,12 +9,16 @@
 // 2 CTAs of 7 warps) instead of padding to 256.
 // Round-1 version on the warp-level tensor-core path (mma.sync m16n8k16); attention is ~4% of the
 // block's FLOPs. Replaces HF eager_attention_forward (see pe_attention in the header).
+#include <cstdlib>
+
 #include "../../include/pipeedge_b200.h"
 #include "common.cuh"
 
 namespace pe {
 
 void count_launches(int n);
+int attention_tcgen05_impl(const void* qkv, void* ctx, int batch, int tokens, int heads, int head_dim,
+                           cudaStream_t stream);
 
 constexpr int kAttnKc = 64;
 constexpr int kAttnMaxWarps = 8;
@@ -275,6 +279,14 @@ static int launch_attention(const void* qkv, void* ctx, int batch, int tokens, i
 int attention_impl(const void* qkv, void* ctx, int batch, int tokens, int heads, int head_dim, cudaStream_t stream) {
   PE_REQUIRE(qkv && ctx, "pe_attention: null pointer");
   PE_REQUIRE(batch > 0 && tokens > 0 && heads > 0, "pe_attention: bad shape");
+  static const int use_tcgen05 = [] {
+    const char* e = getenv("PE_ATTN_TCGEN05");
+    return (e != nullptr && e[0] == '1') ? 1 : 0;     // opt-in until validated on hardware
+  }();
+  if (use_tcgen05) {   // shapes the tcgen05 kernel does not take (head_dim != 64, S > 256) fall through
+    const int rc = attention_tcgen05_impl(qkv, ctx, batch, tokens, heads, head_dim, stream);
+    if (rc != PE_ERR_INVALID) return rc;
+  }
   if (head_dim == 64) return launch_attention<64>(qkv, ctx, batch, tokens, heads, stream);
   if (head_dim == 80) return launch_attention<80>(qkv, ctx, batch, tokens, heads, stream);
   set_error("pe_attention: head_dim=%d unsupported (64 and 80 are built)", head_dim);

@@ -173,3 +173,38 @@ def test_linear_forced_tile_plans(ops, plan, monkeypatch):
         got = ops.linear(a.cuda(), w.cuda(), bias.cuda(), epi)
         tol = 2e-3 if 'F16' in epi_name else 5e-5
         torch.testing.assert_close(got.cpu().float(), want, rtol=tol, atol=tol)
+
+
+_TCGEN05_ATTENTION_CHECK = """
+import os, sys, torch
+import torch.nn.functional as F
+sys.path.insert(0, sys.argv[1])
+os.environ['PE_ATTN_TCGEN05'] = '1'
+from pipeedge_b200 import ops
+for batch, tokens, heads in [(2, 197, 12), (1, 128, 2), (3, 17, 2), (1, 64, 1), (1, 65, 1), (2, 198, 12), (1, 1, 1),
+                             (1, 256, 2), (8, 197, 12), (4, 240, 3), (32, 128, 12), (16, 197, 16)]:
+    gen = torch.Generator().manual_seed(tokens + heads)
+    hidden = heads * 64
+    qkv = (torch.randn(batch * tokens, 3 * hidden, generator=gen) * 1.5).half()
+    q, k, v = [t.float().view(batch, tokens, heads, 64).transpose(1, 2) for t in qkv.split(hidden, dim=1)]
+    probs = F.softmax(torch.matmul(q, k.transpose(2, 3)) * 0.125, dim=-1)
+    want = torch.matmul(probs, v).transpose(1, 2).reshape(batch * tokens, hidden)
+    got = ops.attention(qkv.cuda(), batch, tokens, heads)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(got.cpu().float(), want, rtol=2e-3, atol=2e-3, msg=lambda m: f"{(batch, tokens, heads)}: {m}")
+    print('shape ok', batch, tokens, heads, flush=True)
+print('all ok')
+"""
+
+
+def test_attention_tcgen05(ops):
+    """The tcgen05 / TMEM attention kernel (S and P in TMEM, V read MN-major from the TMA image) against fp32 maths over
+    S in {1 .. 256} incl. the ViT / DeiT / BERT shapes. The library reads its kernel selector once per process, so the
+    check runs in a child process with PE_ATTN_TCGEN05=1."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, '-c', _TCGEN05_ATTENTION_CHECK, root], capture_output=True, text=True,
+                         timeout=600)
+    assert res.returncode == 0 and 'all ok' in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
