@@ -459,7 +459,14 @@ def run_gpu(args, spec, ubatch, seq, qbit, metric, unit, workload):
                 barrier()
                 return wall, tim
 
-            run_phase(warmup, False)
+            wall_w, _ = run_phase(warmup, False)
+            # ... and keep going (untimed) until the GPU has been busy for ~0.3 s: W micro-batches are a few ms of
+            # work, not enough for the clocks to leave their idle state
+            extra = 0
+            if rank == 0:
+                per_step = max(wall_w / warmup, 1e-4)
+                extra = int(min(2000, max(0.0, 0.3 - wall_w) / per_step))
+            run_phase(max(extra, 1), False)
             with ClockSampler(local) as clocks:
                 _, tim = run_phase(steps, False)
             ms_rank = max(tim['compute_ms'], tim['results_ms'])

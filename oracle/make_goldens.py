@@ -207,6 +207,9 @@ def main():
         for name in sys.argv[2:]:
             golden_tiny(name)
         return
+    if sys.argv[1:] == ['vit-large']:
+        golden_full('google/vit-large-patch16-224', 2, (24, 48, 72, 96))
+        return
     golden_adaptive()
     golden_quant()
     for name in ('test/vit-tiny', 'test/deit-tiny', 'test/bert-tiny', 'test/vit-huge-tiny'):
@@ -214,6 +217,7 @@ def main():
     golden_full('google/vit-base-patch16-224', 2, (2, 24, 48))
     golden_full('facebook/deit-base-distilled-patch16-224', 2, (6, 24, 48))
     golden_full('textattack/bert-base-uncased-CoLA', 2, (6, 24, 48), seq_len=128)
+    golden_full('google/vit-large-patch16-224', 2, (24, 48, 72, 96))    # BASELINE config 3's model and 4-way cuts
 
 
 if __name__ == '__main__':

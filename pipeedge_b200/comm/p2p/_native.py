@@ -184,13 +184,13 @@ class NativeStage:
             if shard.native_needs_resize(ubatch, dim1) and self.graph_kernels:
                 check(LIB.pe_pipe_invalidate(self._pipe))   # the stage's workspace is about to be re-created
                 self.graph_kernels.clear()
-            ins = self._inputs.get((ubatch, dim1))
-            if ins is None:
-                ins = [torch.zeros(shape, dtype=dtype, device=torch.device('cuda', self._device))
-                       for shape, dtype in shard.native_input_spec(ubatch, dim1)]
-                self._inputs[(ubatch, dim1)] = ins
             bit, clamp = self._quant()
             with torch.cuda.stream(self._stream):
+                ins = self._inputs.get((ubatch, dim1))
+                if ins is None:     # zero-filled (valid token ids / finite activations for the eager run below)
+                    ins = [torch.zeros(shape, dtype=dtype, device=torch.device('cuda', self._device))
+                           for shape, dtype in shard.native_input_spec(ubatch, dim1)]
+                    self._inputs[(ubatch, dim1)] = ins
                 # eager run on the same buffers first: sizes every persistent buffer and does all first-use work
                 # (module loads, function attributes, tensor-map driver entry points) outside the capture
                 shard.native_forward(ins)

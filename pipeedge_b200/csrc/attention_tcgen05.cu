@@ -1,8 +1,10 @@
 // Unmasked multi-head self-attention on the 5th-gen tensor cores (tcgen05 + TMEM), head_dim 64, S <= 256 keys
 // (PE_ATTN_TCGEN05=0 selects the mma.sync kernel of attention.cu instead). DESIGN.md section 4.
 //
-// One CTA per (128 query rows, head, item); 5 warps: warps 0-3 own the 128 TMEM lanes (one query row per thread),
-// warp 4 issues the TMA loads and the MMAs.
+// One CTA per (128 query rows, head, item); 9 warps: warps 0-7 do the softmax and the epilogue - TWO threads per query
+// row (warps w and w + 4 may touch the same 32 TMEM lanes; each takes half of the key chunks and half of the output
+// columns: with one thread per row the ~200 dependent exp2 / pack steps of a row were the kernel's critical path),
+// warp 8 issues the TMA loads and the MMAs.
 //   1. Q [128 x 64], K [kpad x 64], V [kpad x 64] arrive as three TMA boxes of 128-byte rows (SWIZZLE_128B) through a
 //      3-D tensor map [item][row][3H]: rows past the item's S are out of bounds inside the item -> zero-filled.
 //   2. S = Q K^T: 4 x tcgen05.mma (M=128, N=kpad, K=16), A and B K-major from shared memory, fp32 in TMEM columns
@@ -29,7 +31,10 @@ constexpr int kD = 64;
 constexpr int kRows = 128;          // query rows per CTA = TMEM lanes
 constexpr int kOCol = 128;          // first TMEM column of O (>= kpad / 2: past the packed P)
 constexpr int kTmem = 256;
-constexpr int kThreads = 5 * 32;
+constexpr int kSoftmaxWarps = 8;    // two threads per query row: warps w and w + 4 share a TMEM lane quarter
+constexpr int kIssueWarp = kSoftmaxWarps;
+constexpr int kThreads = (kSoftmaxWarps + 1) * 32;
+constexpr int kMaxChunksPerThread = 4;   // kpad <= 256 -> 8 chunks of 32 keys, split over the two halves
 
 __device__ __forceinline__ void tma_load_3d_addr(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar_addr, int c0,
                                                  int c1, int c2) {
@@ -58,10 +63,32 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
       : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// named barrier among the softmax warps only (the issue warp never joins it)
+__device__ __forceinline__ void softmax_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxWarps * 32) : "memory"); }
 
 __host__ __device__ constexpr uint32_t idesc_f16(int m, int n, int b_mn_major) {
   return (1u << 4) | (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// 2^x for x <= 0 on the SFU (2 ulp): the probabilities are rounded to fp16 right after
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// One 32-key chunk of a score row out of TMEM (the last chunk may hold only 16 keys: kpad % 32 == 16).
+__device__ __forceinline__ void load_scores(uint32_t taddr, bool full, uint32_t pad_bits, uint32_t (&r)[32]) {
+  if (full) {
+    tmem_ld_32x32b_x32(taddr, r);
+  } else {
+    uint32_t h[16];
+    tmem_ld_32x32b_x16(taddr, h);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { r[i] = h[i]; r[16 + i] = pad_bits; }
+  }
+  tmem_wait_ld();
 }
 
 __global__ void __launch_bounds__(kThreads, 2)
@@ -70,6 +97,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_loaded, bar_s, bar_p, bar_o;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_max[2][kRows], s_sum[2][kRows];
   pdl_launch_dependents();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -80,16 +108,16 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
   const uint32_t sk = sq + kRows * 128;                                 // kpad rows x 128 B
   const uint32_t sv = sk + static_cast<uint32_t>((kpad * 128 + 1023) & ~1023);
 
-  if (threadIdx.x == 4 * 32) {
+  if (threadIdx.x == kIssueWarp * 32) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_kv);
     mbar_init(&bar_loaded, 1);
     mbar_init(&bar_s, 1);
-    mbar_init(&bar_p, 4);          // one arrival per softmax warp
+    mbar_init(&bar_p, kSoftmaxWarps);   // one arrival per softmax warp
     mbar_init(&bar_o, 1);
     fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == kIssueWarp) {
     tmem_alloc(&tmem_base_smem, kTmem);
     tmem_relinquish();
   }
@@ -99,7 +127,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
   const uint32_t tmem_base = tmem_base_smem;
   pdl_wait();                                                           // qkv is the predecessor's output
 
-  if (warp == 4) {
+  if (warp == kIssueWarp) {
     // ------------------------------------------------------------ loads + MMA issue (converged, one lane issues)
     if (elect_one()) {
       const uint32_t bytes = static_cast<uint32_t>(kRows + 2 * kpad) * 128u;
@@ -133,61 +161,61 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------ softmax + epilogue: thread = query row
-    const int row = q0 + warp * 32 + lane;
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    // ------------------------------------------------------------ softmax + epilogue: two threads per query row
+    // Warps w and w + 4 own the same 32 TMEM lanes (rows); `half` picks which key chunks (and which 32 output columns)
+    // a thread handles. The row maximum and sum are combined through shared memory.
+    const int quarter = warp & 3, half = warp >> 2;
+    const int r_local = quarter * 32 + lane;
+    const int row = q0 + r_local;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int nchunks = (kpad + 31) >> 5;                               // the last chunk may be half (kpad % 32 == 16)
+    const int c_split = (nchunks + 1) >> 1;
+    const int c_begin = half ? c_split : 0, c_end = half ? nchunks : c_split;
     mbar_wait(&bar_s, 0);
     tcgen05_fence_after();
-    const int nchunks = (kpad + 31) >> 5;                               // the last chunk may be half (kpad % 32 == 16)
     float mx = -INFINITY;
-    for (int c = 0; c < nchunks; ++c) {
-      uint32_t r[32];
-      if (c * 32 + 32 <= kpad) {
-        tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c * 32), r);
-      } else {
-        uint32_t h[16];
-        tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>(c * 32), h);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { r[i] = h[i]; r[16 + i] = 0xff800000u; }   // -inf
+    for (int i = 0; i < kMaxChunksPerThread; ++i) {
+      const int c = c_begin + i;
+      if (c < c_end) {
+        uint32_t r[32];
+        load_scores(t_row + static_cast<uint32_t>(c * 32), c * 32 + 32 <= kpad, 0xff800000u, r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c * 32 + j < tokens) mx = fmaxf(mx, __uint_as_float(r[j]));
       }
-      tmem_wait_ld();
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (c * 32 + i < tokens) mx = fmaxf(mx, __uint_as_float(r[i]));
     }
+    s_max[half][r_local] = mx;
+    softmax_barrier();
+    mx = fmaxf(s_max[0][r_local], s_max[1][r_local]);
     const float msc = mx * scale_log2e;
     float sum = 0.f;
-    for (int c = 0; c < nchunks; ++c) {
-      uint32_t r[32];
-      const bool full = c * 32 + 32 <= kpad;
-      if (full) {
-        tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c * 32), r);
-      } else {
-        uint32_t h[16];
-        tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>(c * 32), h);
+    uint32_t pk[kMaxChunksPerThread][16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { r[i] = h[i]; r[16 + i] = 0; }
-      }
-      tmem_wait_ld();
-      uint32_t pk[16];
+    for (int i = 0; i < kMaxChunksPerThread; ++i) {
+      const int c = c_begin + i;
+      if (c < c_end) {
+        uint32_t r[32];
+        load_scores(t_row + static_cast<uint32_t>(c * 32), c * 32 + 32 <= kpad, 0u, r);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int key = c * 32 + 2 * i;
-        const float p0 = key < tokens ? exp2f(__uint_as_float(r[2 * i]) * scale_log2e - msc) : 0.f;
-        const float p1 = key + 1 < tokens ? exp2f(__uint_as_float(r[2 * i + 1]) * scale_log2e - msc) : 0.f;
-        const __half2 h2 = __floats2half2_rn(p0, p1);
-        // the P.V product sees the ROUNDED probabilities: sum those, as the mma.sync kernel does implicitly? No - it
-        // sums the fp32 values; keep that convention so that both kernels agree to rounding.
-        sum += p0 + p1;
-        pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+        for (int j = 0; j < 16; ++j) {
+          const int key = c * 32 + 2 * j;
+          const float p0 = key < tokens ? fast_exp2(__uint_as_float(r[2 * j]) * scale_log2e - msc) : 0.f;
+          const float p1 = key + 1 < tokens ? fast_exp2(__uint_as_float(r[2 * j + 1]) * scale_log2e - msc) : 0.f;
+          const __half2 h2 = __floats2half2_rn(p0, p1);
+          sum += p0 + p1;
+          pk[i][j] = *reinterpret_cast<const uint32_t*>(&h2);
+        }
       }
-      // in place: columns [16c, 16c+16) have been read already (chunk floor(c/2) <= c)
-      if (full) {
-        tmem_st_32x32b_x16(t_row + static_cast<uint32_t>(c * 16), pk);
-      } else {
-        // half chunk: 16 keys = 8 packed columns; write 16 anyway (the upper 8 are zeros and lie inside [0, kpad))
-        tmem_st_32x32b_x16(t_row + static_cast<uint32_t>(c * 16), pk);
-      }
+    }
+    s_sum[half][r_local] = sum;
+    // P overwrites S in place (packed pairs: chunk c -> columns [16c, 16c + 16)): every thread must have finished
+    // READING its score columns before anyone writes
+    softmax_barrier();
+#pragma unroll
+    for (int i = 0; i < kMaxChunksPerThread; ++i) {
+      const int c = c_begin + i;
+      if (c < c_end) tmem_st_32x32b_x16(t_row + static_cast<uint32_t>(c * 16), pk[i]);
     }
     tmem_wait_st();
     tcgen05_fence_before();
@@ -195,29 +223,26 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
     if (lane == 0) mbar_arrive(&bar_p);
     mbar_wait(&bar_o, 0);
     tcgen05_fence_after();
-    const float inv = 1.0f / sum;
-    __half* out = ctx + (static_cast<size_t>(item) * tokens + row) * hidden + static_cast<size_t>(head) * kD;
+    const float inv = 1.0f / (s_sum[0][r_local] + s_sum[1][r_local]);
+    __half* out = ctx + (static_cast<size_t>(item) * tokens + row) * hidden + static_cast<size_t>(head) * kD + half * 32;
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(kOCol + half * 32), r);
+    tmem_wait_ld();
+    if (row < tokens) {
 #pragma unroll
-    for (int c = 0; c < kD / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(kOCol + c * 32), r);
-      tmem_wait_ld();
-      if (row < tokens) {
+      for (int j = 0; j < 4; ++j) {
+        uint4 v;
+        __half2* h2 = reinterpret_cast<__half2*>(&v);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 v;
-          __half2* h2 = reinterpret_cast<__half2*>(&v);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            h2[i] = __floats2half2_rn(__uint_as_float(r[8 * j + 2 * i]) * inv, __uint_as_float(r[8 * j + 2 * i + 1]) * inv);
-          *reinterpret_cast<uint4*>(out + c * 32 + j * 8) = v;
-        }
+        for (int i = 0; i < 4; ++i)
+          h2[i] = __floats2half2_rn(__uint_as_float(r[8 * j + 2 * i]) * inv, __uint_as_float(r[8 * j + 2 * i + 1]) * inv);
+        *reinterpret_cast<uint4*>(out + j * 8) = v;
       }
     }
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kIssueWarp) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, kTmem);
   }

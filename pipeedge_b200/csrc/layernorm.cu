@@ -21,22 +21,35 @@ constexpr int kLnWarpsPerBlock = 4;
 // t = x (+ resid); optionally sum_out = t (the updated fp32 residual stream); then LayerNorm(t).
 // Folding the residual add in here keeps it out of the GEMM epilogues, where each lane owns a different ROW
 // and a residual read costs 32 cache lines per instruction; here a warp reads whole rows.
+// kVec = float4s per lane (hidden <= kVec * 128): sized per model width so that the row AND its gamma / beta slices stay
+// in registers. gamma / beta are model weights, so they are fetched BEFORE the programmatic dependency on the
+// producing kernel resolves: their L2 latency overlaps the predecessor's tail instead of following the statistics.
+template <int kVec>
 __global__ void __launch_bounds__(kLnWarpsPerBlock * 32)
 layernorm_kernel(const float* __restrict__ x, const float* resid, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, float* sum_out, float* out_f32, __half* out_f16, int rows,
                  int hidden) {
   pdl_launch_dependents();
+  const int lane = threadIdx.x & 31;
+  const int nvec = hidden >> 2;  // hidden % 4 == 0 enforced by the host
+  float4 gv[kVec], bv[kVec];
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nvec) {
+      gv[i] = __ldg(reinterpret_cast<const float4*>(gamma) + idx);
+      bv[i] = __ldg(reinterpret_cast<const float4*>(beta) + idx);
+    }
+  }
   pdl_wait();
   const int row = blockIdx.x * kLnWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= rows) return;
-  const int lane = threadIdx.x & 31;
-  const int nvec = hidden >> 2;  // hidden % 4 == 0 enforced by the host
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * hidden);
   const float4* rr = resid != nullptr ? reinterpret_cast<const float4*>(resid + static_cast<size_t>(row) * hidden) : nullptr;
-  float4 v[kLnMaxVec];
+  float4 v[kVec];
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
+  for (int i = 0; i < kVec; ++i) {
     const int idx = lane + i * 32;
     if (idx < nvec) {
       v[i] = xr[idx];
@@ -51,7 +64,7 @@ layernorm_kernel(const float* __restrict__ x, const float* resid, const float* _
   const float mean = warp_sum(sum) / static_cast<float>(hidden);
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
+  for (int i = 0; i < kVec; ++i) {
     const int idx = lane + i * 32;
     if (idx < nvec) {
       const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
@@ -60,13 +73,11 @@ layernorm_kernel(const float* __restrict__ x, const float* resid, const float* _
   }
   const float var = warp_sum(sq) / static_cast<float>(hidden);
   const float rstd = 1.0f / sqrtf(var + eps);
-  const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
+  for (int i = 0; i < kVec; ++i) {
     const int idx = lane + i * 32;
     if (idx < nvec) {
-      const float4 g = __ldg(g4 + idx), b = __ldg(b4 + idx);
+      const float4 g = gv[i], b = bv[i];
       float4 o;
       o.x = (v[i].x - mean) * rstd * g.x + b.x;
       o.y = (v[i].y - mean) * rstd * g.y + b.y;
@@ -91,8 +102,14 @@ int layernorm_impl(const void* x, const void* resid, const void* gamma, const vo
              "pe_layernorm: hidden=%d must be a multiple of 4 and <= %d", hidden, kLnMaxVec * 128);
   const int grid = (rows + kLnWarpsPerBlock - 1) / kLnWarpsPerBlock;
   static bool configured = false;
-  if (!configured) { prefer_max_shared(layernorm_kernel); configured = true; }
-  PE_CUDA(launch_pdl(layernorm_kernel, dim3(grid), dim3(kLnWarpsPerBlock * 32), 0, stream,
+  if (!configured) {
+    prefer_max_shared(layernorm_kernel<6>);
+    prefer_max_shared(layernorm_kernel<8>);
+    prefer_max_shared(layernorm_kernel<kLnMaxVec>);
+    configured = true;
+  }
+  auto kernel = hidden <= 6 * 128 ? layernorm_kernel<6> : (hidden <= 8 * 128 ? layernorm_kernel<8> : layernorm_kernel<kLnMaxVec>);
+  PE_CUDA(launch_pdl(kernel, dim3(grid), dim3(kLnWarpsPerBlock * 32), 0, stream,
                      static_cast<const float*>(x), static_cast<const float*>(resid), static_cast<const float*>(gamma),
                      static_cast<const float*>(beta), eps, static_cast<float*>(sum_out), static_cast<float*>(out_f32),
                      static_cast<__half*>(out_f16), rows, hidden));

@@ -170,6 +170,30 @@ __device__ void get_tensor(const uint8_t* slot, const LinkTensorHdr& th, int ti,
   }
 }
 
+// The wait itself: ONE warp, no shared memory, long back-off. A consumer may sit here for a whole pipeline latency (the
+// data rank waiting for a result) while the same GPU runs another stream's GEMMs, which need every SM's entire shared
+// memory: a waiting CTA that held shared memory (or many waiting CTAs) would push a GEMM CTA into a second wave.
+__global__ void __launch_bounds__(32) link_wait_kernel(const LinkRx rx, unsigned long long timeout_ns) {
+  if (threadIdx.x == 0) {
+    const uint64_t seq = *reinterpret_cast<volatile uint64_t*>(rx.seq);
+    const uint64_t slot = seq % static_cast<uint64_t>(rx.n_slots), k = seq / static_cast<uint64_t>(rx.n_slots);
+    const uint64_t* flag = rx.full + slot;
+    if (ld_acquire_sys(flag) >= k + 1) return;
+    const unsigned long long t0 = globaltimer_ns();
+    unsigned ns = 64;
+    while (ld_acquire_sys(flag) < k + 1) {
+      __nanosleep(ns);
+      if (ns < 2048) ns <<= 1;
+      if (globaltimer_ns() - t0 > timeout_ns) {
+        *reinterpret_cast<volatile unsigned*>(rx.status) = kLinkErrWaitFull;
+        __threadfence_system();
+        printf("pipeedge_b200: link wait timed out (consumer, slot %llu)\n", static_cast<unsigned long long>(slot));
+        __trap();
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kGetThreads) link_get_kernel(const GetArgs g) {
   extern __shared__ float get_lut[];
   __shared__ uint64_t s_seq;
@@ -630,6 +654,7 @@ static void preload_kernels() {
   if (done) return;
   cudaFuncAttributes attr;
   cudaFuncGetAttributes(&attr, link_get_kernel);
+  cudaFuncGetAttributes(&attr, link_wait_kernel);
   cudaFuncGetAttributes(&attr, link_put_copy_kernel);
   cudaFuncGetAttributes(&attr, link_put_staged_kernel);
   cudaFuncGetAttributes(&attr, link_put_quant_kernel<2>);
@@ -800,6 +825,9 @@ int link_put(pe_link* l, const PutTensor* t, int n_tensors, int items, int bit, 
 }
 
 static int launch_get(pe_link* l, const GetArgs& g, size_t work_units, bool may_decode, cudaStream_t stream) {
+  link_wait_kernel<<<1, 32, 0, stream>>>(g.rx, g.timeout_ns);   // the get kernel below then finds its flag raised
+  PE_CUDA(cudaGetLastError());
+  count_launches(1);
   size_t want = (work_units + kGetThreads - 1) / kGetThreads;
   const int grid = static_cast<int>(want < 1 ? 1 : (want > static_cast<size_t>(2 * sm_count()) ? 2 * sm_count() : want));
   const size_t smem = may_decode ? 4096 * sizeof(float) : 0;   // LUT of 2^bit values for bit <= 12

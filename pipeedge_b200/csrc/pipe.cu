@@ -217,6 +217,8 @@ int pe_pipe_capture_end(pe_pipe* p, const void* a0, const void* b0, size_t n0, c
   const cudaError_t inst = cudaGraphInstantiate(&g.exec, graph, 0);
   cudaGraphDestroy(graph);
   PE_CUDA(inst);
+  PE_CUDA(cudaGraphUpload(g.exec, p->compute));   // the first replay must not pay for moving the graph to the device
+  PE_CUDA(cudaStreamSynchronize(p->compute));
   g.kernels = static_cast<int>(launch_count_now() - p->cap_launch0);
   {
     std::lock_guard<std::mutex> lock(p->graphs_mu);

@@ -40,7 +40,7 @@ def test_tiny_every_sublayer_boundary(name):
     torch.testing.assert_close(whole, torch.from_numpy(g['logits_whole']), rtol=2e-5, atol=2e-5)
 
 
-@pytest.mark.parametrize('name', ['google/vit-base-patch16-224',
+@pytest.mark.parametrize('name', ['google/vit-base-patch16-224', 'google/vit-large-patch16-224',
                                   'facebook/deit-base-distilled-patch16-224',
                                   'textattack/bert-base-uncased-CoLA'])
 def test_full_size_models(name):

@@ -24,6 +24,7 @@ def _worker(rank, world, port, name, cuts, qbits, n_ubatch, ubatch, out_q, nativ
     import sys
     import threading
     faulthandler.enable()   # a native crash prints every thread's Python stack into the test log
+    faulthandler.dump_traceback_later(240, exit=True)   # a hung rank shows where, and ends (instead of the whole test run)
     sys.path.insert(0, ROOT)
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
@@ -74,6 +75,7 @@ def _worker(rank, world, port, name, cuts, qbits, n_ubatch, ubatch, out_q, nativ
             else:
                 assert stop.wait(420)
                 stage.check_workers()
+    faulthandler.cancel_dump_traceback_later()
     out_q.close()
     out_q.join_thread()
     sys.stdout.flush()
@@ -127,7 +129,7 @@ def _run_pipeline(name, cuts, qbits, n_ubatch, ubatch, native):
     for p in procs:
         p.start()
     try:
-        got = out_q.get(timeout=900)   # a fresh box pages torch in for a minute per process
+        got = out_q.get(timeout=300)   # a fresh box pages torch in for a minute per process
     finally:
         for r, p in enumerate(procs):
             p.join(180)
