@@ -7,7 +7,7 @@ forward and the QuantPipe clamp / quantise / bit-pack (and its inverse).
 Only `tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference` legs of
 `bench.py` may import it, and only as the checker or the timed CPU baseline - never as the thing
 shipped. Nothing under `pipeedge_b200/`, `runtime.py`, `model_cfg.py` or `devices.py` imports it;
-`tests/test_layout.py` enforces that.
+`tests/test_host_cpu.py::test_product_never_imports_the_oracle` enforces that.
 
 Where the arithmetic lives
 --------------------------

@@ -89,6 +89,9 @@ class _NativeHop:
 
     @staticmethod
     def _arrays(tensors):
+        for t in tensors:
+            if not t.is_contiguous():   # data_ptr + numel * element_size below describes contiguous memory only
+                raise ValueError("hop payloads must be contiguous tensors (as the reference's Gloo send requires)")
         n = len(tensors)
         ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in tensors])
         sizes = (ctypes.c_size_t * n)(*[t.numel() * t.element_size() for t in tensors])
@@ -383,6 +386,7 @@ class TensorSendThread(AbstractTensorExchangeThread):
         self._dst_rank = dst_rank
         self._last_sig = None
         self._last_cpu: List[torch.Tensor] = []
+        self._last_cpu_versions: List[int] = []
         self._sock = None
         self._hop = None
         self._inflight = collections.deque()
@@ -424,16 +428,18 @@ class TensorSendThread(AbstractTensorExchangeThread):
                 self._report_timed(drain=True)
             except Exception:   # pylint: disable=broad-except
                 logger.exception("hop timing hook failed during shutdown")
-            try:   # tell the receiver this hop is closing, so that its blocking receive returns
-                self._sock.sendall(_ENV_HEAD.pack(-1, 0))
-            except OSError:
-                pass
+            if self._sock is not None:   # (None when open_hop itself failed)
+                try:   # tell the receiver this hop is closing, so that its blocking receive returns
+                    self._sock.sendall(_ENV_HEAD.pack(-1, 0))
+                except OSError:
+                    pass
             if self._hop is not None:
                 self._hop.close()                    # both ends now destroy the hop's communicator at about the same time
-            try:
-                self._sock.close()
-            except OSError:
-                pass
+            if self._sock is not None:
+                try:
+                    self._sock.close()
+                except OSError:
+                    pass
 
     def open_hop(self) -> None:
         """Connect to the receiver and, on a GPU, join the hop's NCCL communicator (blocks until the peer does)."""
@@ -446,13 +452,16 @@ class TensorSendThread(AbstractTensorExchangeThread):
         steady-state header."""
         same_sig = sig == self._last_sig
         last_cpu = self._last_cpu
-        if same_sig and len(cpu) == len(last_cpu) and all(a is b for a, b in zip(cpu, last_cpu)):
+        versions = [t._version for t in cpu]   # pylint: disable=protected-access
+        if same_sig and len(cpu) == len(last_cpu) and all(a is b for a, b in zip(cpu, last_cpu)) and \
+                versions == self._last_cpu_versions:    # same objects AND not written in place since they were sent
             if not defer_fast:
                 self._sock.sendall(_ENV_HEAD.pack(0, -1))   # steady state: nothing but the header
             return True
         meta = b'' if same_sig else pickle.dumps(sig)
         self._last_sig = sig
         self._last_cpu = list(cpu)   # keeps the objects alive, so `is` cannot match a recycled id
+        self._last_cpu_versions = versions
         parts = [t.contiguous().view(-1).view(torch.uint8).numpy().tobytes() for t in cpu if t.numel() > 0]
         blob_len = sum(len(part) for part in parts)
         self._sock.sendall(b''.join([_ENV_HEAD.pack(len(meta), blob_len), meta, *parts]))
@@ -726,6 +735,10 @@ class TensorWorkThread(threading.Thread):
                     done = None
                     if payload.on_consumed is not None:
                         payload.on_consumed(None)
+                # A shard that writes its outputs into a ring of persistent buffers (CUDA-graph mode) must not reuse
+                # a buffer before the hop has sent it: the sender's "sent" event goes back to the shard.
+                guard = getattr(self._callback, 'output_guard', None)
+                sent_cb = guard() if callable(guard) else None
             except BaseException as exc:   # pylint: disable=broad-except
                 # the reference loses worker exceptions and hangs; keep it for the owner to re-raise
                 self.exception = exc
@@ -738,7 +751,7 @@ class TensorWorkThread(threading.Thread):
                         if self._evt_stop_thread.is_set():
                             return
                         self._queue_out.condition.wait(0.05)
-                    self._queue_out.put(_Payload(result, done))
+                    self._queue_out.put(_Payload(result, done, sent_cb))
                     self._queue_out.condition.notify_all()
 
 
@@ -839,6 +852,9 @@ class DistP2pPipelineStage:
             self._queues['out'] = self._queues['in']   # relay without a worker
         else:
             self._threads['work'] = TensorWorkThread(self._queues['in'], self._queues['out'], work_cb)
+            if hasattr(work_cb, 'num_slots'):
+                # outputs in flight between the worker and the wire: queued + being sent + being produced
+                work_cb.num_slots = max(int(work_cb.num_slots), 2 * depth + 3)
         if results_cb is not None:
             queue_res = self._queues['out'] if rank_dst is None else self._queues['res']
             self._threads['res'] = TensorWorkThread(queue_res, None, results_cb)

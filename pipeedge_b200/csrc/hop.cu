@@ -43,26 +43,28 @@ struct NcclApi {
   bool ok = false;
 };
 
-static NcclApi& nccl() {
-  static NcclApi api;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (h == nullptr) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-    if (h != nullptr) {
-      api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
-      api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
-      api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
-      api.Send = reinterpret_cast<decltype(api.Send)>(dlsym(h, "ncclSend"));
-      api.Recv = reinterpret_cast<decltype(api.Recv)>(dlsym(h, "ncclRecv"));
-      api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(dlsym(h, "ncclGroupStart"));
-      api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(dlsym(h, "ncclGroupEnd"));
-      api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
-      api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.GroupStart &&
-               api.GroupEnd && api.GetErrorString;
-    }
+static NcclApi load_nccl() {
+  NcclApi api;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (h == nullptr) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (h != nullptr) {
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    api.Send = reinterpret_cast<decltype(api.Send)>(dlsym(h, "ncclSend"));
+    api.Recv = reinterpret_cast<decltype(api.Recv)>(dlsym(h, "ncclRecv"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(dlsym(h, "ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(dlsym(h, "ncclGroupEnd"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.GroupStart &&
+             api.GroupEnd && api.GetErrorString;
   }
+  return api;
+}
+
+// function-local static: initialised exactly once even when the send and the receive thread race to the first call
+static NcclApi& nccl() {
+  static NcclApi api = load_nccl();
   return api;
 }
 

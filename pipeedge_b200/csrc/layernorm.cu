@@ -46,16 +46,29 @@ layernorm_kernel(const float* __restrict__ x, const float* resid, const float* _
   if (row >= rows) return;
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * hidden);
   const float4* rr = resid != nullptr ? reinterpret_cast<const float4*>(resid + static_cast<size_t>(row) * hidden) : nullptr;
-  float4 v[kVec];
+  // Every load of the row (and of its residual) is issued before the first use: sum_out may alias resid, so the
+  // compiler cannot hoist a later row load above an earlier sum_out store by itself, and a warp that stalls on its
+  // first add with two loads in flight leaves the kernel latency-bound (ncu r02b: 1.0 TB/s).
+  float4 v[kVec], rv[kVec];
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nvec) v[i] = xr[idx];
+  }
+  if (rr != nullptr) {
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+      const int idx = lane + i * 32;
+      if (idx < nvec) rv[i] = rr[idx];
+    }
+  }
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < kVec; ++i) {
     const int idx = lane + i * 32;
     if (idx < nvec) {
-      v[i] = xr[idx];
       if (rr != nullptr) {
-        const float4 r = rr[idx];
-        v[i].x += r.x; v[i].y += r.y; v[i].z += r.z; v[i].w += r.w;
+        v[i].x += rv[i].x; v[i].y += rv[i].y; v[i].z += rv[i].z; v[i].w += rv[i].w;
         if (sum_out != nullptr) reinterpret_cast<float4*>(sum_out + static_cast<size_t>(row) * hidden)[idx] = v[i];
       }
       sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);

@@ -104,6 +104,22 @@ struct GetArgs {
   unsigned long long timeout_ns;
 };
 
+// Grid-stride copy with kU independent 16-byte loads in flight per thread (a lone load per trip left these kernels
+// latency-bound: ncu r02b measured 0.5 TB/s for a 4.8 MB payload).
+template <typename Load, typename Store>
+__device__ __forceinline__ void stream4(size_t n, size_t tid, size_t stride, Load load, Store store) {
+  constexpr int kU = 4;
+  size_t i = tid;
+  for (; i + (kU - 1) * stride < n; i += kU * stride) {
+    uint4 v[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) v[u] = load(i + u * stride);
+#pragma unroll
+    for (int u = 0; u < kU; ++u) store(i + u * stride, v[u]);
+  }
+  for (; i < n; i += stride) store(i, load(i));
+}
+
 __device__ void get_tensor(const uint8_t* slot, const LinkTensorHdr& th, int ti, int items, float* dst, float* lut) {
   const size_t n = th.n;
   const size_t total = static_cast<size_t>(items) * n;
@@ -113,18 +129,21 @@ __device__ void get_tensor(const uint8_t* slot, const LinkTensorHdr& th, int ti,
   if (th.bit == 0) {
     if (th.dtype == 0) {
       const size_t n4 = total >> 2;
-      const float4* s4 = reinterpret_cast<const float4*>(data);
-      float4* d4 = reinterpret_cast<float4*>(dst);
-      for (size_t i = tid; i < n4; i += stride) d4[i] = __ldcg(s4 + i);
+      const uint4* s4 = reinterpret_cast<const uint4*>(data);
+      uint4* d4 = reinterpret_cast<uint4*>(dst);
+      stream4(n4, tid, stride, [&](size_t i) { return __ldcg(s4 + i); }, [&](size_t i, uint4 v) { d4[i] = v; });
       for (size_t i = (n4 << 2) + tid; i < total; i += stride) dst[i] = __ldcg(reinterpret_cast<const float*>(data) + i);
     } else {
-      const size_t n2 = total >> 1;
-      const __half2* s2 = reinterpret_cast<const __half2*>(data);
-      for (size_t i = tid; i < n2; i += stride) {
-        const unsigned raw = __ldcg(reinterpret_cast<const unsigned*>(s2) + i);
-        reinterpret_cast<float2*>(dst)[i] = __half22float2(*reinterpret_cast<const __half2*>(&raw));
-      }
-      if ((total & 1) && tid == 0) dst[total - 1] = __half2float(reinterpret_cast<const __half*>(data)[total - 1]);
+      const size_t n8 = total >> 3;   // 8 halves (16 bytes) in, 32 bytes out
+      const uint4* s4 = reinterpret_cast<const uint4*>(data);
+      stream4(n8, tid, stride, [&](size_t i) { return __ldcg(s4 + i); },
+              [&](size_t i, uint4 v) {
+                const __half2* h = reinterpret_cast<const __half2*>(&v);
+                const float2 a = __half22float2(h[0]), b = __half22float2(h[1]), c = __half22float2(h[2]), d = __half22float2(h[3]);
+                reinterpret_cast<float4*>(dst)[2 * i] = make_float4(a.x, a.y, b.x, b.y);
+                reinterpret_cast<float4*>(dst)[2 * i + 1] = make_float4(c.x, c.y, d.x, d.y);
+              });
+      for (size_t i = (n8 << 3) + tid; i < total; i += stride) dst[i] = __half2float(reinterpret_cast<const __half*>(data)[i]);
     }
     return;
   }
@@ -143,29 +162,51 @@ __device__ void get_tensor(const uint8_t* slot, const LinkTensorHdr& th, int ti,
   const size_t wpi = (n + ratio - 1) / ratio;
   const size_t words = static_cast<size_t>(items) * wpi;
   const uint32_t* codes = reinterpret_cast<const uint32_t*>(data);
-  const bool vec4 = (ratio % 4 == 0) && (n % ratio == 0);
+  if ((ratio % 4 == 0) && (n % ratio == 0) && (wpi % 4 == 0) && words < (1ull << 32)) {
+    // fast path: a thread turns 16 bytes of codes (4 words) into 4 * ratio values; 32-bit index arithmetic
+    const uint32_t wpi4 = static_cast<uint32_t>(wpi >> 2), total4 = static_cast<uint32_t>(words >> 2);
+    const uint4* c4 = reinterpret_cast<const uint4*>(codes);
+    constexpr int kU = 2;
+    const uint32_t t32 = static_cast<uint32_t>(tid), s32 = static_cast<uint32_t>(stride);
+    for (uint32_t g0 = t32; g0 < total4; g0 += kU * s32) {
+      uint4 w[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u)
+        if (g0 + u * s32 < total4) w[u] = __ldcg(c4 + g0 + u * s32);
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const uint32_t g = g0 + u * s32;
+        if (g >= total4) break;
+        const uint32_t item = g / wpi4, in_item = g - item * wpi4;
+        const float sc = __ldcg(scale + item), sh = __ldcg(shift + item);
+        float* oi = dst + static_cast<size_t>(item) * n + static_cast<size_t>(in_item) * 4 * ratio;
+        const uint32_t ww[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          for (int j = 0; j < ratio; j += 4) {
+            float v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t c = (ww[k] >> ((j + q) * bit)) & mask;
+              v[q] = dequant_value(use_lut ? lut[c] : dequant_unit(c, levels), sc, sh);
+            }
+            *reinterpret_cast<float4*>(oi + k * ratio + j) = make_float4(v[0], v[1], v[2], v[3]);
+          }
+        }
+      }
+    }
+    return;
+  }
   for (size_t w = tid; w < words; w += stride) {
     const size_t item = w / wpi;
     const size_t wi = w - item * wpi;
     const uint32_t word = __ldcg(codes + w);
     const float sc = __ldcg(scale + item), sh = __ldcg(shift + item);
     float* oi = dst + item * n + wi * ratio;
-    if (vec4) {
-      for (int j = 0; j < ratio; j += 4) {
-        float v[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t c = (word >> ((j + q) * bit)) & mask;
-          v[q] = dequant_value(use_lut ? lut[c] : dequant_unit(c, levels), sc, sh);
-        }
-        *reinterpret_cast<float4*>(oi + j) = make_float4(v[0], v[1], v[2], v[3]);
-      }
-    } else {
-      for (int j = 0; j < ratio; ++j) {
-        if (wi * ratio + j >= n) break;
-        const uint32_t c = (word >> (j * bit)) & mask;
-        oi[j] = dequant_value(use_lut ? lut[c] : dequant_unit(c, levels), sc, sh);
-      }
+    for (int j = 0; j < ratio; ++j) {
+      if (wi * ratio + j >= n) break;
+      const uint32_t c = (word >> (j * bit)) & mask;
+      oi[j] = dequant_value(use_lut ? lut[c] : dequant_unit(c, levels), sc, sh);
     }
   }
 }
@@ -212,8 +253,9 @@ __global__ void __launch_bounds__(kGetThreads) link_get_kernel(const GetArgs g) 
     const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
     const uint8_t* data = base + kLinkHeaderBytes;
     const size_t n16 = g.n0 >> 4;
-    for (size_t i = tid; i < n16; i += stride)
-      reinterpret_cast<uint4*>(g.dst0)[i] = __ldcg(reinterpret_cast<const uint4*>(data) + i);
+    const uint4* s4 = reinterpret_cast<const uint4*>(data);
+    uint4* d4 = reinterpret_cast<uint4*>(g.dst0);
+    stream4(n16, tid, stride, [&](size_t i) { return __ldcg(s4 + i); }, [&](size_t i, uint4 v) { d4[i] = v; });
     for (size_t i = (n16 << 4) + tid; i < g.n0; i += stride)
       reinterpret_cast<uint8_t*>(g.dst0)[i] = __ldcg(data + i);
   } else {
@@ -337,19 +379,33 @@ __global__ void __launch_bounds__(kPutThreads) link_put_copy_kernel(const PutArg
   const float4* a4 = reinterpret_cast<const float4*>(p.t.a);
   const float4* b4 = reinterpret_cast<const float4*>(p.t.b);
   uint8_t* data = base + p.data_off;
-  for (size_t i = tid; i < n4; i += stride) {
-    float4 v = a4[i];
-    if (b4 != nullptr) {
-      const float4 w = b4[i];
-      v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
-    }
-    if (p.wire_f16) {
-      uint2 pk;
-      *reinterpret_cast<__half2*>(&pk.x) = __floats2half2_rn(v.x, v.y);
-      *reinterpret_cast<__half2*>(&pk.y) = __floats2half2_rn(v.z, v.w);
-      reinterpret_cast<uint2*>(data)[i] = pk;
-    } else {
-      reinterpret_cast<float4*>(data)[i] = v;
+  {
+    constexpr int kU = 4;   // independent loads in flight per thread (see stream4)
+    for (size_t i0 = tid; i0 < n4; i0 += kU * stride) {
+      float4 va[kU], vb[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u)
+        if (i0 + u * stride < n4) va[u] = a4[i0 + u * stride];
+      if (b4 != nullptr) {
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+          if (i0 + u * stride < n4) vb[u] = b4[i0 + u * stride];
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const size_t i = i0 + u * stride;
+        if (i >= n4) break;
+        float4 v = va[u];
+        if (b4 != nullptr) { v.x += vb[u].x; v.y += vb[u].y; v.z += vb[u].z; v.w += vb[u].w; }
+        if (p.wire_f16) {
+          uint2 pk;
+          *reinterpret_cast<__half2*>(&pk.x) = __floats2half2_rn(v.x, v.y);
+          *reinterpret_cast<__half2*>(&pk.y) = __floats2half2_rn(v.z, v.w);
+          reinterpret_cast<uint2*>(data)[i] = pk;
+        } else {
+          reinterpret_cast<float4*>(data)[i] = v;
+        }
+      }
     }
   }
   for (size_t i = (n4 << 2) + tid; i < total; i += stride) {
@@ -426,22 +482,34 @@ __global__ void __launch_bounds__(kPutThreads, 1) link_put_quant_kernel(const Pu
       const float4* a4 = reinterpret_cast<const float4*>(p.t.a + static_cast<size_t>(item) * n + begin);
       const float4* b4 = p.t.b != nullptr ? reinterpret_cast<const float4*>(p.t.b + static_cast<size_t>(item) * n + begin) : nullptr;
       const uint32_t off4 = static_cast<uint32_t>(local) * per4;
-      for (uint32_t i = threadIdx.x; i < len4; i += kPutThreads) {
-        float4 v = a4[i];
-        if (b4 != nullptr) {
-          const float4 w = b4[i];
-          v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
-        }
-        if (p.cache) cache4[swz(off4 + i)] = v;
-        const float e[4] = {v.x, v.y, v.z, v.w};
+      constexpr int kU = 4;   // independent 16-byte loads in flight per thread and operand
+      for (uint32_t i0 = threadIdx.x; i0 < len4; i0 += kU * kPutThreads) {
+        float4 va[kU], vb[kU];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          mn = fminf(mn, e[j]);
-          mx = fmaxf(mx, e[j]);
-          const double d = static_cast<double>(e[j]);
-          s += d;
-          ss += d * d;
-          ss32 += static_cast<double>(__fmul_rn(e[j], e[j]));
+        for (int u = 0; u < kU; ++u)
+          if (i0 + u * kPutThreads < len4) va[u] = a4[i0 + u * kPutThreads];
+        if (b4 != nullptr) {
+#pragma unroll
+          for (int u = 0; u < kU; ++u)
+            if (i0 + u * kPutThreads < len4) vb[u] = b4[i0 + u * kPutThreads];
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const uint32_t i = i0 + u * kPutThreads;
+          if (i >= len4) break;
+          float4 v = va[u];
+          if (b4 != nullptr) { v.x += vb[u].x; v.y += vb[u].y; v.z += vb[u].z; v.w += vb[u].w; }
+          if (p.cache) cache4[swz(off4 + i)] = v;
+          const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            mn = fminf(mn, e[j]);
+            mx = fmaxf(mx, e[j]);
+            const double d = static_cast<double>(e[j]);
+            s += d;
+            ss += d * d;
+            ss32 += static_cast<double>(__fmul_rn(e[j], e[j]));
+          }
         }
       }
     }
@@ -780,25 +848,15 @@ int link_put(pe_link* l, const PutTensor* t, int n_tensors, int items, int bit, 
     } else {
       // generic bit-widths / shapes: the stand-alone kernels quantise into local staging, one kernel ships it
       const float* x = t[ti].a;
+      const size_t codes_bytes = roundup(bytes, 256);
+      const size_t need = codes_bytes + 2 * roundup(items * sizeof(float), 256) + 256 + roundup(quant_workspace_bytes(items, t[ti].n), 256);
+      PE_REQUIRE(l->quant_work != nullptr && need <= l->quant_work_bytes / 2 && total * sizeof(float) <= l->add_scratch_bytes,
+                 "pe_link_put: staging buffers of this link are too small for %d items of %zu elements", items, t[ti].n);
       if (t[ti].b != nullptr) {
-        if (l->add_scratch_bytes < total * sizeof(float)) {
-          // (not reached during graph capture in practice: the first, eager forward sizes it)
-          if (l->add_scratch != nullptr) PE_CUDA(cudaFree(l->add_scratch));
-          PE_CUDA(cudaMalloc(reinterpret_cast<void**>(&l->add_scratch), total * sizeof(float)));
-          l->add_scratch_bytes = total * sizeof(float);
-        }
         PE_REQUIRE((total & 3) == 0, "pe_link_put: a + b payloads need a multiple of 4 elements");
         const int rc = add_impl(t[ti].a, t[ti].b, l->add_scratch, total, stream);
         if (rc != PE_OK) return rc;
         x = l->add_scratch;
-      }
-      const size_t codes_bytes = roundup(bytes, 256);
-      const size_t need = codes_bytes + 2 * roundup(items * sizeof(float), 256) + 256 + roundup(quant_workspace_bytes(items, t[ti].n), 256);
-      const size_t slice = roundup(need, 256);
-      if (l->quant_work_bytes < 2 * slice) {
-        if (l->quant_work != nullptr) PE_CUDA(cudaFree(l->quant_work));
-        PE_CUDA(cudaMalloc(&l->quant_work, 2 * slice));
-        l->quant_work_bytes = 2 * slice;
       }
       uint8_t* w = static_cast<uint8_t*>(l->quant_work) + static_cast<size_t>(ti) * (l->quant_work_bytes / 2);
       uint8_t* codes = w;
@@ -824,10 +882,16 @@ int link_put(pe_link* l, const PutTensor* t, int n_tensors, int items, int bit, 
   return PE_OK;
 }
 
-static int launch_get(pe_link* l, const GetArgs& g, size_t work_units, bool may_decode, cudaStream_t stream) {
-  link_wait_kernel<<<1, 32, 0, stream>>>(g.rx, g.timeout_ns);   // the get kernel below then finds its flag raised
-  PE_CUDA(cudaGetLastError());
-  count_launches(1);
+static int launch_get(pe_link* l, const GetArgs& g, size_t work_units, bool may_decode, bool prewait,
+                      cudaStream_t stream) {
+  if (prewait) {
+    // A consumer that may wait long while OTHER streams of this GPU compute (the data rank draining results) parks in
+    // the one-warp kernel; the get kernel below then finds its flag raised. A stage's own compute stream has nothing
+    // else to run while its input is missing, so there the get kernel waits by itself (one launch less per micro-batch).
+    link_wait_kernel<<<1, 32, 0, stream>>>(g.rx, g.timeout_ns);
+    PE_CUDA(cudaGetLastError());
+    count_launches(1);
+  }
   size_t want = (work_units + kGetThreads - 1) / kGetThreads;
   const int grid = static_cast<int>(want < 1 ? 1 : (want > static_cast<size_t>(2 * sm_count()) ? 2 * sm_count() : want));
   const size_t smem = may_decode ? 4096 * sizeof(float) : 0;   // LUT of 2^bit values for bit <= 12
@@ -838,7 +902,8 @@ static int launch_get(pe_link* l, const GetArgs& g, size_t work_units, bool may_
   return PE_OK;
 }
 
-int link_get(pe_link* l, void* dst0, void* dst1, int items, size_t n0, size_t n1, int n_tensors, cudaStream_t stream) {
+int link_get(pe_link* l, void* dst0, void* dst1, int items, size_t n0, size_t n1, int n_tensors, cudaStream_t stream,
+             bool prewait) {
   PE_REQUIRE(l != nullptr && l->is_rx && l->kind != 2, "pe_link_get: not the consumer end of a peer link");
   PE_REQUIRE(dst0 != nullptr && items > 0 && items <= kLinkMaxItems && n0 > 0 && n_tensors >= 1 && n_tensors <= 2 &&
                  (n_tensors == 1 || (dst1 != nullptr && n1 > 0)),
@@ -855,10 +920,10 @@ int link_get(pe_link* l, void* dst0, void* dst1, int items, size_t n0, size_t n1
   g.n_tensors = n_tensors;
   g.raw = 0;
   g.timeout_ns = l->timeout_ns;
-  return launch_get(l, g, static_cast<size_t>(items) * (n0 + g.n1) / 4, true, stream);
+  return launch_get(l, g, static_cast<size_t>(items) * (n0 + g.n1) / 16, true, prewait, stream);
 }
 
-int link_get_raw(pe_link* l, void* dst, size_t bytes, cudaStream_t stream) {
+int link_get_raw(pe_link* l, void* dst, size_t bytes, cudaStream_t stream, bool prewait) {
   PE_REQUIRE(l != nullptr && l->is_rx && dst != nullptr && bytes > 0, "pe_link_get_raw: bad arguments");
   PE_REQUIRE(kLinkHeaderBytes + bytes <= l->slot_bytes, "pe_link_get_raw: %zu bytes exceed the link's slots", bytes);
   PE_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 15) == 0, "pe_link_get_raw: destination must be 16-byte aligned");
@@ -870,7 +935,7 @@ int link_get_raw(pe_link* l, void* dst, size_t bytes, cudaStream_t stream) {
   g.n_tensors = 1;
   g.raw = 1;
   g.timeout_ns = l->timeout_ns;
-  return launch_get(l, g, bytes / 16, false, stream);
+  return launch_get(l, g, bytes / 64, false, prewait, stream);
 }
 
 // Host-fed link: copy the next payload into the ring (waiting for its slot to be released) and raise its flag, both on
@@ -906,6 +971,19 @@ int link_feed(pe_link* l, const void* src, size_t bytes, int src_is_host, cudaSt
   PE_CUDA(cudaMemcpyAsync(const_cast<uint64_t*>(l->rx.full) + slot, &vals[slot], sizeof(uint64_t), cudaMemcpyHostToDevice,
                           copy_stream));
   ++l->fed;
+  return PE_OK;
+}
+
+// Producer-side staging for the generic bit-widths (stand-alone quant kernels quantise into local memory first): sized
+// once for the link's slots, so that nothing is allocated while a stage's graph is being captured.
+static int alloc_staging(pe_link* l) {
+  const size_t payload = l->slot_bytes - kLinkHeaderBytes;
+  l->add_scratch_bytes = roundup(payload, 256);
+  PE_CUDA(cudaMalloc(reinterpret_cast<void**>(&l->add_scratch), l->add_scratch_bytes));
+  // per tensor: codes (at most half of the fp32 payload at 16 bits) + scale / shift / alpha + the statistics workspace
+  const size_t slice = roundup(payload / 2 + 4096 + quant_workspace_bytes(kLinkMaxItems, 1), 256);
+  l->quant_work_bytes = 2 * slice;
+  PE_CUDA(cudaMalloc(&l->quant_work, l->quant_work_bytes));
   return PE_OK;
 }
 
@@ -985,6 +1063,8 @@ int pe_link_open(int fd, int is_producer, size_t slot_payload_bytes, int n_slots
     l->tx.free_ = static_cast<const uint64_t*>(l->local_block);
     l->tx.slot_bytes = l->slot_bytes;
     l->tx.n_slots = n_slots;
+    rc = alloc_staging(l);
+    if (rc != PE_OK) { free_link(l); return rc; }
   } else {
     l->is_rx = true;
     HelloMsg hello = {};
@@ -1060,6 +1140,8 @@ int pe_link_open_local(size_t slot_payload_bytes, int n_slots, pe_link** out) {
   l->rx.ring = l->tx.ring = b + 2 * kFlagsBytes;
   l->rx.slot_bytes = l->tx.slot_bytes = l->slot_bytes;
   l->rx.n_slots = l->tx.n_slots = n_slots;
+  rc = alloc_staging(l);
+  if (rc != PE_OK) { free_link(l); return rc; }
   // the two ends need their own sequence / arrival counters
   uint8_t* c = static_cast<uint8_t*>(l->ctl_block);
   l->rx.seq = reinterpret_cast<uint64_t*>(c + 8);
@@ -1136,11 +1218,11 @@ int pe_quant_encode_send(pe_link* link, const void* x, const void* skip, int ite
 }
 
 int pe_link_get(pe_link* link, void* dst0, void* dst1, int items, size_t n0, size_t n1, void* stream) {
-  return pe::link_get(link, dst0, dst1, items, n0, n1, dst1 != nullptr ? 2 : 1, static_cast<cudaStream_t>(stream));
+  return pe::link_get(link, dst0, dst1, items, n0, n1, dst1 != nullptr ? 2 : 1, static_cast<cudaStream_t>(stream), true);
 }
 
 int pe_link_get_raw(pe_link* link, void* dst, size_t bytes, void* stream) {
-  return pe::link_get_raw(link, dst, bytes, static_cast<cudaStream_t>(stream));
+  return pe::link_get_raw(link, dst, bytes, static_cast<cudaStream_t>(stream), true);
 }
 
 int pe_link_feed(pe_link* link, const void* src, size_t bytes, int src_is_host, void* copy_stream) {

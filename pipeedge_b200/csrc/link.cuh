@@ -102,8 +102,10 @@ struct pe_link {
 namespace pe {
 
 int link_put(pe_link* link, const PutTensor* t, int n_tensors, int items, int bit, int clamp, cudaStream_t stream);
-int link_get(pe_link* link, void* dst0, void* dst1, int items, size_t n0, size_t n1, int n_tensors, cudaStream_t stream);
-int link_get_raw(pe_link* link, void* dst, size_t bytes, cudaStream_t stream);
+// prewait: park in the one-warp wait kernel first (consumers that may wait long while other streams compute)
+int link_get(pe_link* link, void* dst0, void* dst1, int items, size_t n0, size_t n1, int n_tensors, cudaStream_t stream,
+             bool prewait);
+int link_get_raw(pe_link* link, void* dst, size_t bytes, cudaStream_t stream, bool prewait);
 int link_feed(pe_link* link, const void* src, size_t bytes, int src_is_host, cudaStream_t copy_stream);
 int link_ticket_send(pe_link* link, long long a, long long b);
 int link_ticket_recv(pe_link* link, long long* out2);   // 0 ok, 1 = peer closed

@@ -177,8 +177,8 @@ int pe_pipe_capture_begin(pe_pipe* p, int ubatch, long long dim1, void* dst0, vo
   p->cap_dim1 = dim1;
   p->cap_launch0 = launch_count_now();
   int rc;
-  if (p->in->kind == 2) rc = link_get_raw(p->in, dst0, raw_bytes, p->compute);
-  else rc = link_get(p->in, dst0, dst1, ubatch, n0, n1, dst1 != nullptr ? 2 : 1, p->compute);
+  if (p->in->kind == 2) rc = link_get_raw(p->in, dst0, raw_bytes, p->compute, false);
+  else rc = link_get(p->in, dst0, dst1, ubatch, n0, n1, dst1 != nullptr ? 2 : 1, p->compute, false);
   if (rc != PE_OK) pe_pipe_capture_abort(p);
   return rc;
 }
@@ -316,7 +316,7 @@ int pe_pipe_next_result(pe_pipe* p, void** host_ptr, int* items, size_t* n_out) 
   *n_out = n;
   const size_t bytes = static_cast<size_t>(ubatch) * n * sizeof(float);
   PE_REQUIRE(bytes <= p->res_cap, "pe_pipe_next_result: result of %zu bytes exceeds the results link's slots", bytes);
-  int rc = link_get(p->res, p->res_dev, nullptr, ubatch, n, 0, 1, p->results);
+  int rc = link_get(p->res, p->res_dev, nullptr, ubatch, n, 0, 1, p->results, true);
   if (rc != PE_OK) return rc;
   PE_CUDA(cudaMemcpyAsync(p->res_host, p->res_dev, bytes, cudaMemcpyDeviceToHost, p->results));
   PE_CUDA(cudaEventRecord(p->ev_res_last, p->results));

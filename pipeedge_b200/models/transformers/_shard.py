@@ -33,6 +33,8 @@ class GpuTransformerShard(ModuleShard):
         self._static = False       # native pipeline capture: single persistent buffers, eager launches, deferred add
         self._deferred = None      # (a, b) device addresses when the last static forward deferred its final add
         self._slot = 0
+        self._slot_sent = {}       # ring slot -> CUDA event recorded once the hop has SENT what the slot held
+        self._last_slot = None
         self._rings = {}
         self._copy_stream = None
         self._h2d_rings = {}
@@ -140,11 +142,29 @@ class GpuTransformerShard(ModuleShard):
             res = self.stage.forward(data, out=out, defer_add=not self.shard_config.is_last)
             self._deferred = self.stage.deferred()
             return res
+        if self.use_cuda_graph:
+            sent = self._slot_sent.pop(self._slot, None)
+            if sent is not None:    # the hop may still be sending what this slot held num_slots forwards ago
+                torch.cuda.current_stream().wait_event(sent)
         res = self.stage.forward(data, out=out, use_graph=self.use_cuda_graph)
         self._mark_inputs_consumed()
         if self.use_cuda_graph:
+            self._last_slot = self._slot
             self._slot = (self._slot + 1) % max(1, self.num_slots)
         return res
+
+    def output_guard(self):
+        """Called by the stage's work thread after a forward: returns `on_sent(event)` through which the send thread
+        reports when the hop has finished with the forward's output buffers (None when outputs are not ring buffers)."""
+        inner = self._inner()
+        if not inner.use_cuda_graph or inner._last_slot is None:   # pylint: disable=protected-access
+            return None
+        slot = inner._last_slot                                    # pylint: disable=protected-access
+
+        def on_sent(event, slot=slot, inner=inner):
+            if event is not None:
+                inner._slot_sent[slot] = event                     # pylint: disable=protected-access
+        return on_sent
 
     # ------------------------------------------------------------------ native pipeline (comm/p2p/_native.py)
     def _inner(self) -> 'GpuTransformerShard':

@@ -163,7 +163,7 @@ def _check_against_local_and_oracle(name, cuts, qbits, n_ubatch, ubatch, got):
     ('test/vit-tiny', (6, 12), (0, 0)),            # mid-block cut after an output projection: deferred residual add
     ('test/vit-tiny', (5, 12), (8, 0)),            # tuple payload (ctx, skip), both quantised by the fused send kernel
     ('test/bert-tiny', (7, 12), (4, 0)),           # tuple payload (inter, data) of a post-LN model, 4-bit
-    ('test/deit-tiny', (4, 8, 12), (8, 6, 0)),     # three ranks, block-boundary cuts, fused 8-bit and staged 6-bit hops
+    ('test/deit-tiny', (4, 6, 8), (8, 6, 0)),      # three ranks (the model has 8 sub-layers): fused 8-bit, staged 6-bit hops
     ('test/vit-tiny', (2, 4, 6, 8, 10, 12), (0, 8, 0, 4, 0, 0)),   # six ranks, every rank a half block
 ])
 def test_native_pipeline_is_bit_identical_to_local_shards(name, cuts, qbits):
