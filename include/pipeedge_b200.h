@@ -45,6 +45,7 @@ extern "C" {
 #define PE_EPI_RESID_F32 2  /* out f32 = . + resid(f32)                  (ViTSelfOutput+skip, ViTOutput; BERT pre-LN sums) */
 #define PE_EPI_F32 3        /* out f32                                   (classifier heads)         */
 #define PE_EPI_TANH_F32 4   /* out f32 = tanh(.)                         (BertPooler)               */
+#define PE_EPI_RESID_LN 5   /* internal to pe_linear_residual_layernorm */
 /* OR-able into `epilogue`: W is not written by any work still pending on `stream` (model weights). The kernel may then
  * stream W into shared memory / L2 before its programmatic dependency on the preceding kernel resolves. */
 #define PE_EPI_STATIC_W 0x100
@@ -78,6 +79,20 @@ int pe_residual_layernorm(const void* y, const void* resid, const void* gamma, c
  * Requires k % 8 == 0 (16-byte TMA row pitch). fp32 accumulation in TMEM. */
 int pe_linear(const void* a, const void* w, const void* bias, const void* resid, void* out, int m, int n, int k,
               int epilogue, void* stream);
+
+/* Projection + residual add + LayerNorm in ONE kernel: v = a @ w^T + bias + resid (f32 [m, n], may alias out_f32), then
+ * LayerNorm(v) over the row. Replaces `ViTSelfOutput.dense` + `data += skip` + `layernorm_after` (`vit.py:62-66`),
+ * `ViTOutput` + the next block's `layernorm_before`, and `LayerNorm(dense(x) + input)` of `BertSelfOutput` /
+ * `BertOutput` (HF modeling_bert.py:294-298,352-356). The CTAs that own one row's column slices form a thread-block
+ * cluster and exchange per-row (mean, M2) through distributed shared memory.
+ *   out_f32 (nullable) = v (f32_is_ln == 0: the pre-LN residual stream) or LayerNorm(v) (f32_is_ln != 0: post-LN)
+ *   out_f16 (nullable) = LayerNorm(v), the next GEMM's A operand
+ * n must split into 1, 2, 4 or 8 column slices of a multiple of 32 and at most 128 columns (pe_linear_ln_cluster(n)
+ * > 0: 768, 1024, 384, 192, 128 ...); other widths use pe_linear + pe_residual_layernorm. */
+int pe_linear_residual_layernorm(const void* a, const void* w, const void* bias, const void* resid, const void* gamma,
+                                 const void* beta, float eps, void* out_f32, int f32_is_ln, void* out_f16, int m, int n,
+                                 int k, int static_w, void* stream);
+int pe_linear_ln_cluster(int n);
 
 /* ---- Unmasked multi-head self-attention --------------------------------------------------------
  * Replaces HF `eager_attention_forward` as invoked by `ViTSelfAttention`/`BertSelfAttention`

@@ -44,6 +44,9 @@ SYMBOLS = {
     'pe_layernorm': (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'pe_residual_layernorm': (c_int, [c_void_p] * 4 + [c_float] + [c_void_p] * 3 + [c_int, c_int, c_void_p]),
     'pe_linear': (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
+    'pe_linear_residual_layernorm': (c_int, [c_void_p] * 6 + [c_float, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                             c_void_p]),
+    'pe_linear_ln_cluster': (c_int, [c_int]),
     'pe_attention': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'pe_cast_f32_to_f16': (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     'pe_cast_f16_to_f32': (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -63,6 +63,10 @@ int require_sm100() {
 int linear_impl(const void* a, const void* w, const void* bias, const void* resid, void* out, int m, int n, int k,
                 int epilogue, int rows_per_item, int out_item_rows, int out_row_offset, int resid_per_item,
                 int static_w, cudaStream_t stream);
+int linear_ln_impl(const void* a, const void* w, const void* bias, const void* resid, const void* gamma, const void* beta,
+                   float eps, void* out_f32, int f32_is_ln, void* out_f16, int m, int n, int k, int static_w,
+                   cudaStream_t stream);
+int linear_ln_cluster(int n);
 int linear_simt_impl(const void* a, const void* w, const void* bias, const void* resid, void* out, int m, int n, int k,
                      int epilogue, cudaStream_t stream);
 int layernorm_impl(const void* x, const void* resid, const void* gamma, const void* beta, float eps, void* sum_out,
@@ -110,6 +114,15 @@ int pe_linear(const void* a, const void* w, const void* bias, const void* resid,
   return pe::linear_impl(a, w, bias, resid, out, m, n, k, epilogue & 0xff, 0, 0, 0, 0,
                          /*static_w=*/(epilogue & PE_EPI_STATIC_W) != 0 ? 1 : 0, static_cast<cudaStream_t>(stream));
 }
+
+int pe_linear_residual_layernorm(const void* a, const void* w, const void* bias, const void* resid, const void* gamma,
+                                 const void* beta, float eps, void* out_f32, int f32_is_ln, void* out_f16, int m, int n,
+                                 int k, int static_w, void* stream) {
+  return pe::linear_ln_impl(a, w, bias, resid, gamma, beta, eps, out_f32, f32_is_ln, out_f16, m, n, k, static_w,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int pe_linear_ln_cluster(int n) { return pe::linear_ln_cluster(n); }
 
 int pe_debug_linear_simt(const void* a, const void* w, const void* bias, const void* resid, void* out, int m, int n,
                          int k, int epilogue, void* stream) {

@@ -281,7 +281,7 @@ int attention_impl(const void* qkv, void* ctx, int batch, int tokens, int heads,
   PE_REQUIRE(batch > 0 && tokens > 0 && heads > 0, "pe_attention: bad shape");
   static const int use_tcgen05 = [] {
     const char* e = getenv("PE_ATTN_TCGEN05");
-    return (e != nullptr && e[0] == '1') ? 1 : 0;     // opt-in until validated on hardware
+    return (e != nullptr && e[0] == '0') ? 0 : 1;     // PE_ATTN_TCGEN05=0 selects the mma.sync kernel below
   }();
   if (use_tcgen05) {   // shapes the tcgen05 kernel does not take (head_dim != 64, S > 256) fall through
     const int rc = attention_tcgen05_impl(qkv, ctx, batch, tokens, heads, head_dim, stream);

@@ -29,6 +29,7 @@
 
 #include "../../include/pipeedge_b200.h"
 #include "common.cuh"
+#include "ln_dev.cuh"
 
 namespace pe {
 
@@ -71,7 +72,16 @@ struct GemmParams {
   int resid_per_item;  // 1: resid is [out_item_rows, n] shared by all items
   int stg_offset;      // byte offset of the epilogue staging from the ring base: 0 = aliases the ring (one tile per CTA)
   int static_w;        // 1: W is not written by anything still pending on the stream -> may be read before pdl_wait()
+  // PE_EPI_RESID_LN: v = A W^T + bias + resid, then LayerNorm(v) over the full row (the CN CTAs of a cluster own a row)
+  const float* ln_gamma;
+  const float* ln_beta;
+  float ln_eps;
+  int ln_off;          // byte offset (from the ring base) of the row-statistics exchange area
+  int f32_is_ln;       // the fp32 output (tm_out) carries LayerNorm(v) (post-LN models) instead of v (pre-LN models)
+  int has_f32, has_f16;
 };
+
+constexpr int kLnAreaBytes = 8192;   // [4][128] float2 chunk statistics + [2][128] float2 CTA statistics (double-buffered)
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 // Epilogue GELU (exact-erf form, as the reference's nn.GELU): |error| <= 7e-7 absolute, 4e-6 relative - far below the
@@ -217,12 +227,14 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmParams& p, const floa
 template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                    const __grid_constant__ CUtensorMap tm_out, const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_out2,
+                    const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ __align__(8) uint64_t ln_bar[2];     // PE_EPI_RESID_LN: "every CTA of the row has published its statistics"
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5;
@@ -255,6 +267,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], kNumEpiWarps);
+      mbar_init(&ln_bar[s], static_cast<uint32_t>(p.cn));
     }
     fence_barrier_init();
   }
@@ -450,6 +463,140 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     float* stg = reinterpret_cast<float*>(smem_gen + p.stg_offset) + warp * kStgFloatsPerWarp;
     int acc = 0;
     uint32_t acc_phase = 0;
+    if (EPI == PE_EPI_RESID_LN) {
+      // ---- projection + residual add + LayerNorm in one epilogue. The CN CTAs of a cluster hold the CN column slices
+      // (BN <= 128: one 32-column chunk per warp) of the same 128 rows. Per row: every thread reduces its 32 values to
+      // (mean, M2); chunks are merged per CTA, CTAs exchange (mean, M2) through distributed shared memory (one remote
+      // mbarrier arrival per peer), merged in rank order with Chan's update - every CTA derives bit-identical row
+      // statistics. Then v (or LayerNorm(v)) goes out as fp32 and LayerNorm(v) as fp16 through the TMA-store boxes.
+      float2* ln_part = reinterpret_cast<float2*>(smem_gen + p.ln_off);   // [4 chunk groups][128 rows]
+      float2* ln_cta = ln_part + 4 * kBlockM;                             // [2][128], double-buffered by tile parity
+      const bool active = group < chunks;
+      const int r_local = quarter * 32 + lane;
+      const float inv_n = 1.0f / static_cast<float>(p.n);
+      uint8_t* box = reinterpret_cast<uint8_t*>(stg);
+      const uint32_t box_addr = smem_u32(box);
+      int par = 0;
+      uint32_t ln_phase[2] = {0u, 0u};
+      for (int sup = cluster_id; sup < num_supers; sup += num_clusters) {
+        const int m_blk = (sup % p.num_super_m) * p.cm + m_rank;
+        const int n_blk = (sup / p.num_super_m) * p.cn + n_rank;
+        mbar_wait_relaxed(&tmem_full_bar[acc], acc_phase);
+        tcgen05_fence_after();
+        const int row0 = m_blk * kBlockM + quarter * 32;
+        const int row = row0 + lane;
+        const int gcol = n_blk * p.block_n + group * 32;
+        float v[32];
+        if (active) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                 static_cast<uint32_t>(acc * kAccStride + group * 32), r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);   // the accumulator lives in registers from here on
+        float mean_c = 0.f, m2_c = 0.f;
+        if (active) {
+          if (row < p.m) {
+            const float4* r4 = reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(row) * p.n + gcol);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {     // two batches of four independent 16-byte residual loads
+              float4 rv[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) rv[i] = r4[4 * h + i];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int c = 4 * (4 * h + i);
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol) + 4 * h + i);
+                v[c] = __fadd_rn(__fadd_rn(v[c], b4.x), rv[i].x); v[c + 1] = __fadd_rn(__fadd_rn(v[c + 1], b4.y), rv[i].y);
+                v[c + 2] = __fadd_rn(__fadd_rn(v[c + 2], b4.z), rv[i].z); v[c + 3] = __fadd_rn(__fadd_rn(v[c + 3], b4.w), rv[i].w);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          }
+          ln_chunk32(v, mean_c, m2_c);
+        }
+        ln_part[group * kBlockM + r_local] = make_float2(mean_c, m2_c);
+        named_barrier<2>(kNumEpiWarps * 32);
+        if (group == 0) {   // this CTA's slice of the row: merge its chunks in column order
+          float cnt = 32.f, mean = mean_c, m2 = m2_c;
+          for (int c = 1; c < chunks; ++c) {
+            const float2 q = ln_part[c * kBlockM + r_local];
+            ln_merge(cnt, mean, m2, 32.f, q.x, q.y);
+          }
+          ln_cta[par * kBlockM + r_local] = make_float2(mean, m2);
+        }
+        named_barrier<3>(kNumEpiWarps * 32);
+        if (warp == 0 && lane < p.cn)   // tell every CTA of the row (incl. this one) that my statistics are published
+          mbar_arrive_cluster(mapa_shared(smem_u32(&ln_bar[par]), static_cast<uint32_t>(lane)));
+        mbar_wait_cluster(&ln_bar[par], ln_phase[par]);
+        ln_phase[par] ^= 1u;
+        float cnt = 0.f, mean = 0.f, m2 = 0.f;
+        {
+          const uint32_t mine = smem_u32(&ln_cta[par * kBlockM + r_local]);
+          const float bn = static_cast<float>(p.block_n);
+          for (int j = 0; j < p.cn; ++j) {     // slices in column order (cluster rank = slice index)
+            const float2 q = ld_dsmem_f2(mapa_shared(mine, static_cast<uint32_t>(j)));
+            ln_merge(cnt, mean, m2, bn, q.x, q.y);
+          }
+        }
+        const float rstd = ln_rstd(m2, inv_n, p.ln_eps);
+        if (active) {
+          uint8_t* my_row128 = box + lane * 128;
+          uint8_t* my_row64 = box + lane * 64;
+          const int sw128 = lane & 7, sw64 = (lane >> 1) & 3;
+          // normalised values are recomputed where they are needed instead of being kept beside v (register budget: 96)
+          auto norm4 = [&](int i) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + gcol) + i);
+            const float4 e4 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + gcol) + i);
+            return make_float4(ln_apply(v[4 * i], mean, rstd, g4.x, e4.x), ln_apply(v[4 * i + 1], mean, rstd, g4.y, e4.y),
+                               ln_apply(v[4 * i + 2], mean, rstd, g4.z, e4.z), ln_apply(v[4 * i + 3], mean, rstd, g4.w, e4.w));
+          };
+          if (p.has_f32) {
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 o = p.f32_is_ln ? norm4(j) : make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              *reinterpret_cast<float4*>(my_row128 + ((j ^ sw128) << 4)) = o;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && row0 < p.m) {
+              tma_store_2d(&tm_out, box_addr, gcol, row0);
+              tma_store_commit();
+            }
+          }
+          if (p.has_f16) {
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 lo = norm4(2 * j), hi = norm4(2 * j + 1);
+              uint4 pk;
+              __half2* h2 = reinterpret_cast<__half2*>(&pk);
+              h2[0] = __floats2half2_rn(lo.x, lo.y); h2[1] = __floats2half2_rn(lo.z, lo.w);
+              h2[2] = __floats2half2_rn(hi.x, hi.y); h2[3] = __floats2half2_rn(hi.z, hi.w);
+              *reinterpret_cast<uint4*>(my_row64 + ((j ^ sw64) << 4)) = pk;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && row0 < p.m) {
+              tma_store_2d(&tm_out2, box_addr, gcol, row0);
+              tma_store_commit();
+            }
+          }
+        }
+        par ^= 1;
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    } else
     for (int sup = cluster_id; sup < num_supers; sup += num_clusters) {
       const int m_blk = (sup % p.num_super_m) * p.cm + m_rank;
       const int n_blk = (sup / p.num_super_m) * p.cn + n_rank;
@@ -665,8 +812,8 @@ GemmPlan plan_gemm(int m, int n, int k, int epilogue) {
 }
 
 template <int EPI>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmParams& p,
-                       cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& tout2,
+                       const GemmParams& p, cudaStream_t stream) {
   static bool configured = false;
   // the attribute bounds DYNAMIC shared memory; static barriers live outside it (227 KiB total per CTA)
   const int max_smem = kPipeSmemBudget + kStgBytes + 1024;
@@ -676,7 +823,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   }
   const uint32_t stage_bytes = kABytes + static_cast<uint32_t>(p.block_n) * (kBlockK * 2);
   const size_t ring = static_cast<size_t>(p.stages) * stage_bytes, stg_end = static_cast<size_t>(p.stg_offset) + kStgBytes;
-  const size_t smem = (ring > stg_end ? ring : stg_end) + 1024;
+  size_t smem = (ring > stg_end ? ring : stg_end) + 1024;
+  if (EPI == PE_EPI_RESID_LN) smem = static_cast<size_t>(p.ln_off) + kLnAreaBytes + 1024;
   const int csize = p.cm * p.cn;
   const int supers = p.num_super_m * p.num_super_n;
   const int avail = max_clusters(csize);
@@ -695,13 +843,13 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  PE_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<EPI>, ta, tb, tout, p));
+  PE_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<EPI>, ta, tb, tout, tout2, p));
   count_launches(1);
   return PE_OK;
 }
 
 // Tile grid, ring depth and staging placement that follow from a plan (shared by the launcher and pe_debug_gemm_plan).
-static void fill_geometry(GemmParams& p, const GemmPlan& plan, int m, int n, int k) {
+static void fill_geometry(GemmParams& p, const GemmPlan& plan, int m, int n, int k, int reserve = 0) {
   p.m = m; p.n = n; p.k = k;
   p.block_n = plan.bn;
   p.cm = plan.cm;
@@ -715,7 +863,7 @@ static void fill_geometry(GemmParams& p, const GemmPlan& plan, int m, int n, int
   // ring and the whole 224 KiB go to pipeline depth (BN=256: 4 stages instead of 3). With several tiles per CTA the
   // next tile's loads overlap the epilogue and the two need separate space.
   const bool one_round = p.num_super_m * p.num_super_n <= max_clusters(p.cm * p.cn);
-  int stages = (one_round ? kPipeSmemBudget + kStgBytes : kPipeSmemBudget) / static_cast<int>(stage_bytes);
+  int stages = ((one_round ? kPipeSmemBudget + kStgBytes : kPipeSmemBudget) - reserve) / static_cast<int>(stage_bytes);
   p.stages = stages > kMaxStages ? kMaxStages : (stages < 2 ? 2 : stages);
   if (const char* cap = getenv("PE_GEMM_STAGES")) {   // tuning scripts only
     const int c = atoi(cap);
@@ -775,13 +923,75 @@ int linear_impl(const void* a, const void* w, const void* bias, const void* resi
     if (rc != PE_OK) return rc;
   }
   switch (epilogue) {
-    case PE_EPI_F16: return launch_gemm<PE_EPI_F16>(ta, tb, tout, p, stream);
-    case PE_EPI_GELU_F16: return launch_gemm<PE_EPI_GELU_F16>(ta, tb, tout, p, stream);
-    case PE_EPI_RESID_F32: return launch_gemm<PE_EPI_RESID_F32>(ta, tb, tout, p, stream);
-    case PE_EPI_F32: return launch_gemm<PE_EPI_F32>(ta, tb, tout, p, stream);
-    case PE_EPI_TANH_F32: return launch_gemm<PE_EPI_TANH_F32>(ta, tb, tout, p, stream);
+    case PE_EPI_F16: return launch_gemm<PE_EPI_F16>(ta, tb, tout, tout, p, stream);
+    case PE_EPI_GELU_F16: return launch_gemm<PE_EPI_GELU_F16>(ta, tb, tout, tout, p, stream);
+    case PE_EPI_RESID_F32: return launch_gemm<PE_EPI_RESID_F32>(ta, tb, tout, tout, p, stream);
+    case PE_EPI_F32: return launch_gemm<PE_EPI_F32>(ta, tb, tout, tout, p, stream);
+    case PE_EPI_TANH_F32: return launch_gemm<PE_EPI_TANH_F32>(ta, tb, tout, tout, p, stream);
     default: set_error("pe_linear: unknown epilogue %d", epilogue); return PE_ERR_INVALID;
   }
+}
+
+// Cluster width for the fused projection + residual + LayerNorm: the CN CTAs of a cluster own the CN column slices of a
+// row, each at most 128 columns wide (one 32-column chunk per epilogue warp). 0 = this width is not supported.
+int linear_ln_cluster(int n) {
+  for (int cn = 8; cn >= 1; cn >>= 1)
+    if (n % cn == 0 && (n / cn) % 32 == 0 && n / cn <= 128 && kBlockM % cn == 0) return cn;
+  return 0;
+}
+
+// out_f32 (nullable) = v or LayerNorm(v) (`f32_is_ln`), out_f16 (nullable) = LayerNorm(v), v = a @ w^T + bias + resid.
+int linear_ln_impl(const void* a, const void* w, const void* bias, const void* resid, const void* gamma, const void* beta,
+                   float eps, void* out_f32, int f32_is_ln, void* out_f16, int m, int n, int k, int static_w,
+                   cudaStream_t stream) {
+  PE_REQUIRE(a && w && bias && resid && gamma && beta && (out_f32 || out_f16), "pe_linear_residual_layernorm: null pointer");
+  PE_REQUIRE(m > 0 && n > 0 && k > 0 && (k & 7) == 0, "pe_linear_residual_layernorm: bad shape m=%d n=%d k=%d", m, n, k);
+  const int cn = linear_ln_cluster(n);
+  PE_REQUIRE(cn > 0, "pe_linear_residual_layernorm: n=%d is not supported (needs n = cn * bn, cn in {1,2,4,8}, bn %% 32 == 0, bn <= 128)", n);
+  PE_REQUIRE((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(resid) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(gamma) & 15) == 0 && (reinterpret_cast<uintptr_t>(beta) & 15) == 0 &&
+                 (out_f32 == nullptr || (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0) &&
+                 (out_f16 == nullptr || (reinterpret_cast<uintptr_t>(out_f16) & 15) == 0),
+             "pe_linear_residual_layernorm: operands must be 16-byte aligned");
+  int rc = require_sm100();
+  if (rc != PE_OK) return rc;
+  const GemmPlan plan = {1, cn, n / cn};
+  GemmParams p = {};
+  p.bias = static_cast<const float*>(bias);
+  p.resid = static_cast<const float*>(resid);
+  p.out = out_f32;
+  fill_geometry(p, plan, m, n, k, kLnAreaBytes);
+  p.trace = nullptr;
+  p.debug_mode = 0;
+  p.tma_store = 1;
+  p.static_w = static_w != 0 ? 1 : 0;
+  p.ln_gamma = static_cast<const float*>(gamma);
+  p.ln_beta = static_cast<const float*>(beta);
+  p.ln_eps = eps;
+  p.f32_is_ln = f32_is_ln;
+  p.has_f32 = out_f32 != nullptr;
+  p.has_f16 = out_f16 != nullptr;
+  {
+    const uint32_t stage_bytes = kABytes + static_cast<uint32_t>(p.block_n) * (kBlockK * 2);
+    const size_t ring = static_cast<size_t>(p.stages) * stage_bytes, stg_end = static_cast<size_t>(p.stg_offset) + kStgBytes;
+    p.ln_off = static_cast<int>(((ring > stg_end ? ring : stg_end) + 1023) / 1024 * 1024);
+  }
+  CUtensorMap ta, tb;
+  rc = encode_f16_2d(&ta, a, static_cast<uint64_t>(m), static_cast<uint64_t>(k), static_cast<uint32_t>(kBlockM / p.cn));
+  if (rc != PE_OK) return rc;
+  rc = encode_f16_2d(&tb, w, static_cast<uint64_t>(n), static_cast<uint64_t>(k), static_cast<uint32_t>(p.block_n));
+  if (rc != PE_OK) return rc;
+  CUtensorMap t32 = ta, t16 = ta;
+  if (out_f32 != nullptr) {
+    rc = encode_out_2d(&t32, out_f32, static_cast<uint64_t>(m), static_cast<uint64_t>(n), false);
+    if (rc != PE_OK) return rc;
+  }
+  if (out_f16 != nullptr) {
+    rc = encode_out_2d(&t16, out_f16, static_cast<uint64_t>(m), static_cast<uint64_t>(n), true);
+    if (rc != PE_OK) return rc;
+  }
+  return launch_gemm<PE_EPI_RESID_LN>(ta, tb, t32, t16, p, stream);
 }
 
 // Host-only: the plan and launch geometry pe_linear would use for this shape (no device needed).

@@ -2,11 +2,15 @@
 // one warp per row, 128-bit loads, the row lives in registers between the two statistics passes.
 // Replaces nn.LayerNorm at vit.py:59,66,168 and inside BertSelfOutput/BertOutput/BertEmbeddings.
 #include "../../include/pipeedge_b200.h"
+#include <cstdlib>
+
 #include "common.cuh"
+#include "ln_dev.cuh"
 
 namespace pe {
 
 void count_launches(int n);
+int linear_ln_cluster(int n);
 
 // Every kernel of the stage asks for the same (maximum-shared) L1/shared split as the GEMM and attention kernels:
 // switching the carve-out between consecutive kernels makes the SMs drain and reconfigure.
@@ -107,6 +111,110 @@ layernorm_kernel(const float* __restrict__ x, const float* resid, const float* _
   }
 }
 
+// The stand-alone mirror of the fused projection + residual + LayerNorm epilogue (ln_dev.cuh): one warp per row, one LANE
+// per 32-column chunk (the fused kernel's thread), chunk statistics merged through shuffles in exactly the fused
+// kernel's order (chunks inside a slice, then slices). Used wherever a LayerNorm has no projection of its own stage in
+// front of it - a stage's first sub-layer, the final LayerNorm - when the fused kernel is enabled, so that the result of
+// a pipeline does not depend on where it is cut.
+template <int kCpl>   // chunks per lane: hidden <= kCpl * 1024
+__global__ void __launch_bounds__(kLnWarpsPerBlock * 32)
+layernorm_chunked_kernel(const float* __restrict__ x, const float* resid, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, float eps, float* sum_out, float* out_f32, __half* out_f16,
+                         int rows, int hidden, int slice) {
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31;
+  const int nchunks = hidden >> 5;
+  pdl_wait();
+  const int row = blockIdx.x * kLnWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const size_t base = static_cast<size_t>(row) * hidden;
+  float v[kCpl][32];
+  float mean_c[kCpl], m2_c[kCpl];
+#pragma unroll
+  for (int q = 0; q < kCpl; ++q) {
+    const int c = lane + 32 * q;
+    mean_c[q] = 0.f; m2_c[q] = 0.f;
+    if (c < nchunks) {
+      const float4* x4 = reinterpret_cast<const float4*>(x + base + c * 32);
+      float4 xv[8], rv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xv[i] = x4[i];
+      if (resid != nullptr) {
+        const float4* r4 = reinterpret_cast<const float4*>(resid + base + c * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rv[i] = r4[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (resid != nullptr) {
+          xv[i].x = __fadd_rn(xv[i].x, rv[i].x); xv[i].y = __fadd_rn(xv[i].y, rv[i].y);
+          xv[i].z = __fadd_rn(xv[i].z, rv[i].z); xv[i].w = __fadd_rn(xv[i].w, rv[i].w);
+          if (sum_out != nullptr) reinterpret_cast<float4*>(sum_out + base + c * 32)[i] = xv[i];
+        }
+        v[q][4 * i] = xv[i].x; v[q][4 * i + 1] = xv[i].y; v[q][4 * i + 2] = xv[i].z; v[q][4 * i + 3] = xv[i].w;
+      }
+      ln_chunk32(v[q], mean_c[q], m2_c[q]);
+    }
+  }
+  // merge in the fused kernel's order; every lane computes the same totals
+  const int cps = slice >> 5, nslices = hidden / slice;
+  float cnt = 0.f, mean = 0.f, m2 = 0.f;
+  for (int sidx = 0; sidx < nslices; ++sidx) {
+    float scnt = 0.f, smean = 0.f, sm2 = 0.f;
+    for (int k = 0; k < cps; ++k) {
+      const int c = sidx * cps + k;
+      float mc = 0.f, qc = 0.f;
+#pragma unroll
+      for (int q = 0; q < kCpl; ++q) {
+        const float a = __shfl_sync(0xffffffffu, mean_c[q], c & 31);
+        const float b = __shfl_sync(0xffffffffu, m2_c[q], c & 31);
+        if ((c >> 5) == q) { mc = a; qc = b; }
+      }
+      if (k == 0) { scnt = 32.f; smean = mc; sm2 = qc; }
+      else ln_merge(scnt, smean, sm2, 32.f, mc, qc);
+    }
+    ln_merge(cnt, mean, m2, static_cast<float>(slice), smean, sm2);
+  }
+  const float rstd = ln_rstd(m2, 1.0f / static_cast<float>(hidden), eps);
+#pragma unroll
+  for (int q = 0; q < kCpl; ++q) {
+    const int c = lane + 32 * q;
+    if (c < nchunks) {
+      const float4* g4 = reinterpret_cast<const float4*>(gamma + c * 32);
+      const float4* b4 = reinterpret_cast<const float4*>(beta + c * 32);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {     // 8 columns per trip: two fp32 stores, one fp16 store
+        const float4 ga = __ldg(g4 + 2 * i), gb = __ldg(g4 + 2 * i + 1), ba = __ldg(b4 + 2 * i), bb = __ldg(b4 + 2 * i + 1);
+        const float4 lo = make_float4(ln_apply(v[q][8 * i], mean, rstd, ga.x, ba.x), ln_apply(v[q][8 * i + 1], mean, rstd, ga.y, ba.y),
+                                      ln_apply(v[q][8 * i + 2], mean, rstd, ga.z, ba.z), ln_apply(v[q][8 * i + 3], mean, rstd, ga.w, ba.w));
+        const float4 hi = make_float4(ln_apply(v[q][8 * i + 4], mean, rstd, gb.x, bb.x), ln_apply(v[q][8 * i + 5], mean, rstd, gb.y, bb.y),
+                                      ln_apply(v[q][8 * i + 6], mean, rstd, gb.z, bb.z), ln_apply(v[q][8 * i + 7], mean, rstd, gb.w, bb.w));
+        if (out_f32 != nullptr) {
+          reinterpret_cast<float4*>(out_f32 + base + c * 32)[2 * i] = lo;
+          reinterpret_cast<float4*>(out_f32 + base + c * 32)[2 * i + 1] = hi;
+        }
+        if (out_f16 != nullptr) {
+          uint4 pk;
+          __half2* h2 = reinterpret_cast<__half2*>(&pk);
+          h2[0] = __floats2half2_rn(lo.x, lo.y); h2[1] = __floats2half2_rn(lo.z, lo.w);
+          h2[2] = __floats2half2_rn(hi.x, hi.y); h2[3] = __floats2half2_rn(hi.z, hi.w);
+          reinterpret_cast<uint4*>(out_f16 + base + c * 32)[i] = pk;
+        }
+      }
+    }
+  }
+}
+
+// PE_FUSE_LN=1: projections run with the fused residual + LayerNorm epilogue wherever the stage allows (stage.cu), and the
+// remaining stand-alone LayerNorms use the kernel above so that both paths agree bit for bit.
+bool fuse_ln_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("PE_FUSE_LN");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
+
 int layernorm_impl(const void* x, const void* resid, const void* gamma, const void* beta, float eps, void* sum_out,
                    void* out_f32, void* out_f16, int rows, int hidden, cudaStream_t stream) {
   PE_REQUIRE(x && gamma && beta && (out_f32 || out_f16), "pe_layernorm: null pointer");
@@ -114,6 +222,16 @@ int layernorm_impl(const void* x, const void* resid, const void* gamma, const vo
   PE_REQUIRE(rows > 0 && hidden > 0 && (hidden & 3) == 0 && hidden <= kLnMaxVec * 128,
              "pe_layernorm: hidden=%d must be a multiple of 4 and <= %d", hidden, kLnMaxVec * 128);
   const int grid = (rows + kLnWarpsPerBlock - 1) / kLnWarpsPerBlock;
+  const int cn = linear_ln_cluster(hidden);
+  if (fuse_ln_enabled() && cn > 0 && hidden <= 2048 && (hidden & 31) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    auto kernel = hidden <= 1024 ? layernorm_chunked_kernel<1> : layernorm_chunked_kernel<2>;
+    PE_CUDA(launch_pdl(kernel, dim3(grid), dim3(kLnWarpsPerBlock * 32), 0, stream, static_cast<const float*>(x),
+                       static_cast<const float*>(resid), static_cast<const float*>(gamma), static_cast<const float*>(beta),
+                       eps, static_cast<float*>(sum_out), static_cast<float*>(out_f32), static_cast<__half*>(out_f16), rows,
+                       hidden, hidden / cn));
+    count_launches(1);
+    return PE_OK;
+  }
   static bool configured = false;
   if (!configured) {
     prefer_max_shared(layernorm_kernel<6>);

@@ -11,6 +11,7 @@
 //   t32               f32 [M, H]   output projection / FC2 result before the residual add, which is folded into
 //                                  the LayerNorm that follows (or a small add kernel when the stage ends there)
 // Replaces {ViT,DeiT,Bert}ModelShard.forward's block loop (vit.py:161-170, deit.py:158-167, bert.py:142-151).
+#include <cstdlib>
 #include <map>
 #include <tuple>
 #include <vector>
@@ -25,6 +26,11 @@ int require_sm100();
 int linear_impl(const void* a, const void* w, const void* bias, const void* resid, void* out, int m, int n, int k,
                 int epilogue, int rows_per_item, int out_item_rows, int out_row_offset, int resid_per_item,
                 int static_w, cudaStream_t stream);
+int linear_ln_impl(const void* a, const void* w, const void* bias, const void* resid, const void* gamma, const void* beta,
+                   float eps, void* out_f32, int f32_is_ln, void* out_f16, int m, int n, int k, int static_w,
+                   cudaStream_t stream);
+int linear_ln_cluster(int n);
+bool fuse_ln_enabled();
 int layernorm_impl(const void* x, const void* resid, const void* gamma, const void* beta, float eps, void* sum_out,
                    void* out_f32, void* out_f16, int rows, int hidden, cudaStream_t stream);
 int add_impl(const void* a, const void* b, void* out, size_t n, cudaStream_t stream);
@@ -118,6 +124,11 @@ static int enqueue(pe_stage* st, const void* in0, const void* in1, void* out0, v
   bool pending = false;         // residual stream = t32 + skip, not yet added (pre-LN only)
   bool a16_valid = false;       // a16 holds the f16 copy of x (post-LN only)
 
+  // Projection + residual add + LayerNorm as ONE kernel (cluster epilogue, gemm_tcgen05.cu) wherever the LayerNorm that
+  // follows an output projection / FC2 belongs to this stage and the width splits into <= 8 slices of <= 128 columns.
+  const bool fuse_ln = fuse_ln_enabled() && linear_ln_cluster(H) > 0;
+  bool a16_ready = false;       // pre-LN: a16 already holds LayerNorm(x) for the sub-layer about to run
+
   if (first_sub == 0 || first_sub == 2) {
     x = static_cast<const float*>(in0);
   } else if (first_sub == 1) {
@@ -128,9 +139,11 @@ static int enqueue(pe_stage* st, const void* in0, const void* in1, void* out0, v
     skip = static_cast<const float*>(in1);
   }
 
-  for (const SubRange& r : st->ranges) {
+  for (size_t ri = 0; ri < st->ranges.size(); ++ri) {
+    const SubRange& r = st->ranges[ri];
     const pe_block_weights& w = st->blocks[r.block];
     for (int sub = r.s0; sub <= r.s1; ++sub) {
+      const bool has_next = sub < r.s1 || ri + 1 < st->ranges.size();   // another sub-layer of this stage follows
       const bool attn_half = sub == 0;
       switch (sub) {
         case 0:
@@ -139,6 +152,8 @@ static int enqueue(pe_stage* st, const void* in0, const void* in1, void* out0, v
           const void* ln_b = attn_half ? w.ln1_b : w.ln2_b;
           if (post_ln) {
             if (!a16_valid) { PE_K(PE_KERNEL_CAST, cast_impl(x, st->a16, static_cast<size_t>(M) * H, true, stream)); }
+          } else if (a16_ready) {
+            a16_ready = false;   // the producing projection already wrote x and a16 = LayerNorm(x)
           } else if (pending) {
             // residual add of the previous sub-layer + this LayerNorm in one pass; the sum becomes the stream
             PE_K(PE_KERNEL_LAYERNORM, layernorm_impl(st->t32, skip, ln_w, ln_b, d.eps, resid_dest, nullptr, st->a16, M, H, stream));
@@ -157,6 +172,30 @@ static int enqueue(pe_stage* st, const void* in0, const void* in1, void* out0, v
           break;
         }
         default: {   // 1: output projection, 3: FC2 - both produce t32 = A @ W^T + b, residual add deferred
+          const void* a_op = sub == 1 ? static_cast<const void*>(st->ctx16) : static_cast<const void*>(st->inter16);
+          const void* w_op = sub == 1 ? w.w_o : w.w_fc2;
+          const void* b_op = sub == 1 ? w.b_o : w.b_fc2;
+          const int k_op = sub == 1 ? H : I;
+          const int kind = sub == 1 ? PE_KERNEL_GEMM_OUT : PE_KERNEL_GEMM_FC2;
+          if (fuse_ln && post_ln) {
+            // BertSelfOutput / BertOutput: LayerNorm(dense(a) + input) -> fp32 stream and fp16 operand in one kernel
+            const void* ln_w = sub == 1 ? w.ln1_w : w.ln2_w;
+            const void* ln_b = sub == 1 ? w.ln1_b : w.ln2_b;
+            PE_K(kind, linear_ln_impl(a_op, w_op, b_op, skip, ln_w, ln_b, d.eps, resid_dest, 1, st->a16, M, H, k_op, 1, stream));
+            a16_valid = true;
+            x = resid_dest; skip = nullptr;
+            break;
+          }
+          if (fuse_ln && !post_ln && has_next) {
+            // ViT: x = dense(a) + skip -> the residual stream, and LayerNorm(x) of the sub-layer that follows -> a16
+            const pe_block_weights& wn = sub == 1 ? w : st->blocks[st->ranges[ri + 1].block];
+            const void* ln_w = sub == 1 ? wn.ln2_w : wn.ln1_w;
+            const void* ln_b = sub == 1 ? wn.ln2_b : wn.ln1_b;
+            PE_K(kind, linear_ln_impl(a_op, w_op, b_op, skip, ln_w, ln_b, d.eps, resid_dest, 0, st->a16, M, H, k_op, 1, stream));
+            x = resid_dest; skip = nullptr;
+            a16_ready = true;
+            break;
+          }
           if (sub == 1) {
             PE_K(PE_KERNEL_GEMM_OUT, lin(st->ctx16, w.w_o, w.b_o, nullptr, st->t32, M, H, H, PE_EPI_F32, stream));
           } else {

@@ -93,6 +93,28 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilo
     return out
 
 
+def linear_residual_layernorm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, resid: torch.Tensor,
+                              gamma: torch.Tensor, beta: torch.Tensor, eps: float, f32_is_ln: bool = False,
+                              want_f32: bool = True, want_f16: bool = True, out_f32: Optional[torch.Tensor] = None):
+    """v = a @ w.T + bias + resid, LayerNorm(v) - one kernel (cluster epilogue). Returns (f32 tensor or None, f16 or
+    None): the f32 output is v, or LayerNorm(v) when `f32_is_ln`; `out_f32` may be `resid` itself (in place)."""
+    _want(a, torch.float16, 'a')
+    _want(w, torch.float16, 'w')
+    for name, t in (('bias', bias), ('resid', resid), ('gamma', gamma), ('beta', beta)):
+        _want(t, torch.float32, name)
+    k = a.shape[-1]
+    m = a.numel() // k
+    n = w.shape[0]
+    if LIB.pe_linear_ln_cluster(n) <= 0:
+        raise ValueError(f"linear_residual_layernorm: width {n} is not supported by the fused kernel")
+    o32 = (out_f32 if out_f32 is not None else torch.empty((m, n), dtype=torch.float32, device=a.device)) if want_f32 else None
+    o16 = torch.empty((m, n), dtype=torch.float16, device=a.device) if want_f16 else None
+    check(LIB.pe_linear_residual_layernorm(a.data_ptr(), w.data_ptr(), bias.data_ptr(), resid.data_ptr(), gamma.data_ptr(),
+                                           beta.data_ptr(), float(eps), _ptr(o32), 1 if f32_is_ln else 0, _ptr(o16), m, n, k,
+                                           1, _stream()))
+    return o32, o16
+
+
 def attention(qkv: torch.Tensor, batch: int, tokens: int, heads: int, head_dim: int = 0) -> torch.Tensor:
     """Unmasked MHA over fused qkv f16 [batch*tokens, 3*H]; returns merged-head ctx f16 [batch*tokens, H].
     `head_dim` defaults to H / heads and is only checked against it."""

@@ -179,7 +179,7 @@ _TCGEN05_ATTENTION_CHECK = """
 import os, sys, torch
 import torch.nn.functional as F
 sys.path.insert(0, sys.argv[1])
-os.environ['PE_ATTN_TCGEN05'] = '1'
+os.environ['PE_ATTN_TCGEN05'] = sys.argv[2]
 from pipeedge_b200 import ops
 for batch, tokens, heads in [(2, 197, 12), (1, 128, 2), (3, 17, 2), (1, 64, 1), (1, 65, 1), (2, 198, 12), (1, 1, 1),
                              (1, 256, 2), (8, 197, 12), (4, 240, 3), (32, 128, 12), (16, 197, 16)]:
@@ -197,14 +197,95 @@ print('all ok')
 """
 
 
-def test_attention_tcgen05(ops):
-    """The tcgen05 / TMEM attention kernel (S and P in TMEM, V read MN-major from the TMA image) against fp32 maths over
-    S in {1 .. 256} incl. the ViT / DeiT / BERT shapes. The library reads its kernel selector once per process, so the
-    check runs in a child process with PE_ATTN_TCGEN05=1."""
+@pytest.mark.parametrize('mode', ['1', '0'])
+def test_attention_tcgen05(ops, mode):
+    """Both attention kernels - tcgen05 / TMEM (S and P in TMEM, V read MN-major from the TMA image; the default for
+    head_dim 64, S <= 256) and mma.sync (PE_ATTN_TCGEN05=0; also the fall-back for other shapes) - against fp32 maths over
+    S in {1 .. 256} incl. the ViT / DeiT / BERT shapes. The library reads its selector once per process, so each mode
+    runs in a child process."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    res = subprocess.run([sys.executable, '-c', _TCGEN05_ATTENTION_CHECK, root], capture_output=True, text=True,
+    res = subprocess.run([sys.executable, '-c', _TCGEN05_ATTENTION_CHECK, root, mode], capture_output=True, text=True,
                          timeout=600)
     assert res.returncode == 0 and 'all ok' in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+
+
+@pytest.mark.parametrize('m,n,k', [(1576, 768, 768), (1576, 768, 3072), (3152, 1024, 4096), (130, 128, 512), (300, 192, 768),
+                                   (70, 384, 1536), (4096, 768, 768)])
+@pytest.mark.parametrize('post_ln', [False, True])
+def test_linear_residual_layernorm_fused(ops, m, n, k, post_ln):
+    """Projection + residual add + LayerNorm in one kernel (cluster of the row's column slices exchanging (mean, M2)
+    through distributed shared memory) against fp32 maths on the same fp16 operands: clusters of 8 (768, 1024), 4, 2
+    and 1 CTAs, several row tiles per cluster (4096 rows), a ragged last row tile, and the in-place residual update."""
+    gen = torch.Generator().manual_seed(m + n + k)
+    a = (torch.randn(m, k, generator=gen) * 0.7).half()
+    w = (torch.randn(n, k, generator=gen) * 0.05).half()
+    bias = torch.randn(n, generator=gen) * 0.1
+    resid = torch.randn(m, n, generator=gen) * 1.3 + 0.2
+    gamma = 1.0 + 0.1 * torch.randn(n, generator=gen)
+    beta = 0.1 * torch.randn(n, generator=gen)
+    v = a.float() @ w.float().t() + bias + resid
+    ln = F.layer_norm(v, (n,), gamma, beta, 1e-12)
+    r_dev = resid.cuda()
+    o32, o16 = ops.linear_residual_layernorm(a.cuda(), w.cuda(), bias.cuda(), r_dev, gamma.cuda(), beta.cuda(), 1e-12,
+                                             f32_is_ln=post_ln, out_f32=r_dev)      # in place, as the stage uses it
+    torch.cuda.synchronize()
+    assert o32.data_ptr() == r_dev.data_ptr()
+    torch.testing.assert_close(o32.cpu(), ln if post_ln else v, rtol=2e-4, atol=2e-4)
+    torch.testing.assert_close(o16.cpu().float(), ln, rtol=2e-3, atol=2e-3)
+
+
+_FUSED_LN_CHECK = """
+import os, sys, torch
+sys.path.insert(0, sys.argv[1])
+os.environ['PE_FUSE_LN'] = '1'
+from pipeedge_b200 import _lib, ops
+from pipeedge_b200.models import ModuleShardConfig
+from pipeedge_b200.models.transformers import bert, vit
+from pipeedge_b200.synth import MODEL_SPECS, hf_config, synth_input, synth_weights
+# 1. fused kernel == GEMM (fp32 out) + the stand-alone LayerNorm that mirrors its statistics, bit for bit
+for m, n, k in ((1576, 768, 768), (1576, 768, 3072), (600, 1024, 1024), (130, 128, 512), (300, 192, 768), (4096, 768, 768)):
+    gen = torch.Generator().manual_seed(m + n)
+    a = (torch.randn(m, k, generator=gen) * 0.7).half().cuda()
+    w = (torch.randn(n, k, generator=gen) * 0.05).half().cuda()
+    bias, resid = (torch.randn(n, generator=gen) * 0.1).cuda(), (torch.randn(m, n, generator=gen) * 1.3).cuda()
+    gamma, beta = (1.0 + 0.1 * torch.randn(n, generator=gen)).cuda(), (0.1 * torch.randn(n, generator=gen)).cuda()
+    f32, f16 = ops.linear_residual_layernorm(a, w, bias, resid, gamma, beta, 1e-12)
+    t = ops.linear(a, w, bias, _lib.PE_EPI_F32)
+    s32, l32, l16 = ops.residual_layernorm(t, resid, gamma, beta, 1e-12, want_sum=True, want_f32=True, want_f16=True)
+    p32, _ = ops.linear_residual_layernorm(a, w, bias, resid, gamma, beta, 1e-12, f32_is_ln=True, want_f16=False)
+    torch.cuda.synchronize()
+    assert torch.equal(f32, s32.view(m, n)) and torch.equal(f16, l16.view(m, n)) and torch.equal(p32, l32.view(m, n)), (m, n, k)
+    print('kernel ok', m, n, k, flush=True)
+# 2. a pipeline's result does not depend on where it is cut (fused inside a stage, stand-alone at its edges)
+for name, cls, cuts_list in (('test/vit-tiny', vit.ViTShardForImageClassification, ((12,), (5, 12), (2, 4, 6, 8, 10, 12))),
+                             ('test/bert-tiny', bert.BertShardForSequenceClassification, ((12,), (7, 12), (2, 6, 12)))):
+    spec = MODEL_SPECS[name]
+    weights = synth_weights(spec, seed=0)
+    x = synth_input(spec, 3, seed=5, seq_len=32)
+    outs = []
+    for cuts in cuts_list:
+        data, lo = x, 1
+        for hi in cuts:
+            cfg = ModuleShardConfig(layer_start=lo, layer_end=hi, is_first=lo == 1, is_last=hi == spec.layers)
+            data = cls(hf_config(spec), cfg, weights)(data)
+            lo = hi + 1
+        outs.append(data.cpu())
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0]), name
+    print('partition ok', name, flush=True)
+print('all ok')
+"""
+
+
+def test_fused_layernorm_is_bit_identical_to_its_standalone_mirror(ops):
+    """PE_FUSE_LN=1 (child process): the cluster epilogue and the chunked stand-alone LayerNorm share ln_dev.cuh, so the
+    fused kernel equals GEMM + LayerNorm bit for bit, and a model's logits are the same for every partition."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, '-c', _FUSED_LN_CHECK, root], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and 'all ok' in res.stdout, res.stdout[-3000:] + res.stderr[-4000:]
