@@ -233,10 +233,12 @@ int pe_bert_embed(const void* ids, const void* pos_ids, const void* word, const 
  * little-endian uint32, LSB first) + per-item f32 scale / shift in the slot header. */
 typedef struct pe_link pe_link;
 /* Peer link over `fd`; blocks until the other end has called it too. The producer picks the geometry
- * (`slot_payload_bytes` per slot, `n_slots` in [2,8]); the consumer passes 0, 0. */
-int pe_link_open(int fd, int is_producer, size_t slot_payload_bytes, int n_slots, pe_link** out);
+ * (`slot_payload_bytes` per slot, `n_slots` in [2,8]) and announces the QuantPipe bit-width it expects to send
+ * (`quant_hint`, 0 = raw; it only sizes the consumer's receive grid - every payload describes itself); the consumer
+ * passes 0, 0, 0. */
+int pe_link_open(int fd, int is_producer, size_t slot_payload_bytes, int n_slots, int quant_hint, pe_link** out);
 /* Both ends in this process (one-rank pipelines, tests). */
-int pe_link_open_local(size_t slot_payload_bytes, int n_slots, pe_link** out);
+int pe_link_open_local(size_t slot_payload_bytes, int n_slots, int quant_hint, pe_link** out);
 /* Consumer end fed by the host with pe_link_feed (the data rank's inputs, `devices.forward_pre_hook_to_device`). */
 int pe_link_open_host(size_t slot_payload_bytes, int n_slots, pe_link** out);
 int pe_link_close(pe_link* link);

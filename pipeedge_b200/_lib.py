@@ -71,8 +71,8 @@ SYMBOLS = {
     'pe_hop_send': (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_size_t), c_int, c_void_p, c_void_p, c_void_p, c_int]),
     'pe_hop_wait_envelope': (c_int, [c_void_p, POINTER(c_longlong)]),
     'pe_hop_recv': (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_size_t), POINTER(c_void_p), c_int, c_void_p, c_void_p]),
-    'pe_link_open': (c_int, [c_int, c_int, c_size_t, c_int, POINTER(c_void_p)]),
-    'pe_link_open_local': (c_int, [c_size_t, c_int, POINTER(c_void_p)]),
+    'pe_link_open': (c_int, [c_int, c_int, c_size_t, c_int, c_int, POINTER(c_void_p)]),
+    'pe_link_open_local': (c_int, [c_size_t, c_int, c_int, POINTER(c_void_p)]),
     'pe_link_open_host': (c_int, [c_size_t, c_int, POINTER(c_void_p)]),
     'pe_link_close': (c_int, [c_void_p]),
     'pe_link_slot_bytes': (c_size_t, [c_void_p]),

@@ -91,7 +91,8 @@ class NativeStage:
     def _open_link(self, sock, is_producer: bool, payload_bytes: int) -> ctypes.c_void_p:
         handle = ctypes.c_void_p()
         check(LIB.pe_link_open(sock.fileno(), 1 if is_producer else 0, payload_bytes if is_producer else 0,
-                               link_slots() if is_producer else 0, ctypes.byref(handle)))
+                               link_slots() if is_producer else 0, self._quant()[0] if is_producer else 0,
+                               ctypes.byref(handle)))
         self._links.append(handle)
         return handle
 
@@ -129,7 +130,7 @@ class NativeStage:
             self._link_in = handle
             if peer_out is None:
                 loop = ctypes.c_void_p()
-                check(LIB.pe_link_open_local(out_bytes, link_slots(), ctypes.byref(loop)))
+                check(LIB.pe_link_open_local(out_bytes, link_slots(), 0, ctypes.byref(loop)))
                 self._links.append(loop)
                 self._link_out = self._link_res = loop
             else:

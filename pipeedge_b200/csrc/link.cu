@@ -69,13 +69,18 @@ __device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ uint64_t ld_flag(const uint64_t* p, int relaxed) {
+  // relaxed: a volatile load (never served from L1); payload reads that follow use ld.global.cg, i.e. L2 - the point of
+  // coherence peer and DMA writes land in - so no acquire fence is needed to see the data the flag announces
+  return relaxed ? *reinterpret_cast<const volatile uint64_t*>(p) : ld_acquire_sys(p);
+}
 // Bounded: a protocol bug or a dead peer ends in a trap (the launch fails, the host sees an error), never in a hang.
 __device__ __forceinline__ void spin_until_ge(const uint64_t* flag, uint64_t want, unsigned long long timeout_ns,
-                                              unsigned* status, unsigned code) {
-  if (ld_acquire_sys(flag) >= want) return;
+                                              unsigned* status, unsigned code, int relaxed = 0) {
+  if (ld_flag(flag, relaxed) >= want) return;
   const unsigned long long t0 = globaltimer_ns();
   unsigned ns = 32;
-  while (ld_acquire_sys(flag) < want) {
+  while (ld_flag(flag, relaxed) < want) {
     __nanosleep(ns);
     if (ns < 512) ns <<= 1;
     if (globaltimer_ns() - t0 > timeout_ns) {
@@ -101,6 +106,7 @@ struct GetArgs {
   int items;
   int n_tensors;
   int raw;              // host-fed link: no header, copy n0 bytes
+  int sync_mode;
   unsigned long long timeout_ns;
 };
 
@@ -241,7 +247,7 @@ __global__ void __launch_bounds__(kGetThreads) link_get_kernel(const GetArgs g) 
   if (threadIdx.x == 0) {
     const uint64_t seq = *reinterpret_cast<volatile uint64_t*>(g.rx.seq);
     const uint64_t slot = seq % static_cast<uint64_t>(g.rx.n_slots), k = seq / static_cast<uint64_t>(g.rx.n_slots);
-    spin_until_ge(g.rx.full + slot, k + 1, g.timeout_ns, g.rx.status, kLinkErrWaitFull);
+    spin_until_ge(g.rx.full + slot, k + 1, g.timeout_ns, g.rx.status, kLinkErrWaitFull, g.sync_mode & 1);
     s_seq = seq;
   }
   __syncthreads();
@@ -288,7 +294,7 @@ __global__ void __launch_bounds__(kGetThreads) link_get_kernel(const GetArgs g) 
   // kernels 3-4x longer than their copy (ncu r02c).
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    if (g.sync_mode & 2) __threadfence(); else __threadfence_system();
     const unsigned prev = atomicAdd(g.rx.done_ctr, 1u);
     if (prev == gridDim.x - 1) {
       *g.rx.done_ctr = 0;
@@ -312,6 +318,7 @@ struct PutArgs {
   int chunks;             // fused quantise: segments per item
   size_t per;             // ... elements per segment (multiple of 16)
   int cache;              // ... keep the fp32 slice in shared memory between the passes
+  int sync_mode;
   unsigned long long timeout_ns;
   // staged path (generic bit-widths): codes / scale / shift already computed into local memory
   const uint8_t* staged_codes;
@@ -325,7 +332,7 @@ __device__ __forceinline__ void put_begin(const PutArgs& p, uint64_t* s_seq) {
   if (threadIdx.x == 0) {
     const uint64_t seq = *reinterpret_cast<volatile uint64_t*>(p.tx.seq);
     const uint64_t slot = seq % static_cast<uint64_t>(p.tx.n_slots), k = seq / static_cast<uint64_t>(p.tx.n_slots);
-    spin_until_ge(p.tx.free_ + slot, k, p.timeout_ns, p.tx.status, kLinkErrWaitFree);   // its (k-1)-th use was consumed
+    spin_until_ge(p.tx.free_ + slot, k, p.timeout_ns, p.tx.status, kLinkErrWaitFree, p.sync_mode & 1);   // (k-1)-th use consumed
     *s_seq = seq;
   }
   __syncthreads();
@@ -354,7 +361,7 @@ __device__ __forceinline__ void put_end(const PutArgs& p, uint64_t seq) {
   // CTA to arrive publishes the slot
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    if (p.sync_mode & 2) __threadfence(); else __threadfence_system();
     const unsigned prev = atomicAdd(p.tx.done_ctr, 1u);
     if (prev == gridDim.x - 1) {
       *p.tx.done_ctr = 0;
@@ -716,6 +723,13 @@ static int alloc_common(pe_link* l) {
   preload_kernels();
   const char* w = getenv("PIPEEDGE_WIRE_F16");
   l->wire_f16 = (w != nullptr && w[0] == '1') ? 1 : 0;
+  // Default 2: one GPU-scope fence per CTA, one system-scope fence by the CTA that publishes the slot (the release is
+  // cumulative over what the arrival counter ordered before it). A system-scope fence in every CTA cost 12 us per
+  // send + receive pair of a 4.8 MB payload (profiles/r02_link_bench.txt); PE_LINK_SYNC=0 restores it.
+  const char* sm = getenv("PE_LINK_SYNC");
+  l->sync_mode = sm != nullptr ? atoi(sm) : 2;
+  const char* gc = getenv("PE_LINK_GRID_CAP");
+  l->grid_cap = gc != nullptr ? atoi(gc) : 0;
   return PE_OK;
 }
 
@@ -743,6 +757,8 @@ static void preload_kernels() {
 struct HelloMsg {
   uint32_t magic;
   uint32_t n_slots;
+  uint32_t quant_hint;         // the bit-width the producer expects to send (sizes the consumer's receive grid)
+  uint32_t pad;
   uint64_t slot_bytes;
   cudaIpcMemHandle_t handle;   // the producer's block (free flags)
 };
@@ -810,6 +826,7 @@ int link_put(pe_link* l, const PutTensor* t, int n_tensors, int items, int bit, 
     p.wire_f16 = l->wire_f16;
     p.is_last = ti == n_tensors - 1 ? 1 : 0;
     p.data_off = off;
+    p.sync_mode = l->sync_mode;
     p.timeout_ns = l->timeout_ns;
     const size_t total = static_cast<size_t>(items) * t[ti].n;
     const bool aligned = (reinterpret_cast<uintptr_t>(t[ti].a) & 15) == 0 &&
@@ -817,7 +834,9 @@ int link_put(pe_link* l, const PutTensor* t, int n_tensors, int items, int bit, 
     if (bit == 0) {
       PE_REQUIRE(aligned, "pe_link_put: payload tensors must be 16-byte aligned");
       size_t want = (total / 4 + kPutThreads - 1) / kPutThreads;
-      const int grid = static_cast<int>(want < 1 ? 1 : (want > static_cast<size_t>(2 * sm_count()) ? 2 * sm_count() : want));
+      // half the SMs move a few MB as fast as all of them and pay half the per-CTA arrival / fence cost
+      const size_t cap = l->grid_cap > 0 ? static_cast<size_t>(l->grid_cap) : static_cast<size_t>((sm_count() + 1) / 2);
+      const int grid = static_cast<int>(want < 1 ? 1 : (want > cap ? cap : want));
       link_put_copy_kernel<<<grid, kPutThreads, 0, stream>>>(p);
       PE_CUDA(cudaGetLastError());
       count_launches(1);
@@ -896,7 +915,10 @@ static int launch_get(pe_link* l, const GetArgs& g, size_t work_units, bool may_
     count_launches(1);
   }
   size_t want = (work_units + kGetThreads - 1) / kGetThreads;
-  const int grid = static_cast<int>(want < 1 ? 1 : (want > static_cast<size_t>(2 * sm_count()) ? 2 * sm_count() : want));
+  // copies: half the SMs (see link_put); dequantising payloads (the producer announced them at open) want every SM
+  const size_t cap = l->grid_cap > 0 ? static_cast<size_t>(l->grid_cap)
+                                     : static_cast<size_t>(l->quant_hint > 0 ? 2 * sm_count() : (sm_count() + 1) / 2);
+  const int grid = static_cast<int>(want < 1 ? 1 : (want > cap ? cap : want));
   const size_t smem = may_decode ? 4096 * sizeof(float) : 0;   // LUT of 2^bit values for bit <= 12
   link_get_kernel<<<grid, kGetThreads, smem, stream>>>(g);
   PE_CUDA(cudaGetLastError());
@@ -922,6 +944,7 @@ int link_get(pe_link* l, void* dst0, void* dst1, int items, size_t n0, size_t n1
   g.items = items;
   g.n_tensors = n_tensors;
   g.raw = 0;
+  g.sync_mode = l->sync_mode;
   g.timeout_ns = l->timeout_ns;
   return launch_get(l, g, static_cast<size_t>(items) * (n0 + g.n1) / 16, true, prewait, stream);
 }
@@ -937,6 +960,7 @@ int link_get_raw(pe_link* l, void* dst, size_t bytes, cudaStream_t stream, bool 
   g.items = 1;
   g.n_tensors = 1;
   g.raw = 1;
+  g.sync_mode = l->sync_mode;
   g.timeout_ns = l->timeout_ns;
   return launch_get(l, g, bytes / 64, false, prewait, stream);
 }
@@ -1014,7 +1038,7 @@ extern "C" {
 // Both ends call this once over the hop's connected socket `fd` (it stays owned by the caller and later carries the
 // tickets); blocks until the peer has answered. The PRODUCER chooses the geometry: `slot_bytes` of payload room per slot
 // (the 16 KiB header is added here) and `n_slots`; the consumer passes 0 for both.
-int pe_link_open(int fd, int is_producer, size_t slot_payload_bytes, int n_slots, pe_link** out) {
+int pe_link_open(int fd, int is_producer, size_t slot_payload_bytes, int n_slots, int quant_hint, pe_link** out) {
   using namespace pe;
   PE_REQUIRE(out != nullptr && fd >= 0, "pe_link_open: bad arguments");
   int rc = require_sm100();
@@ -1039,6 +1063,7 @@ int pe_link_open(int fd, int is_producer, size_t slot_payload_bytes, int n_slots
     HelloMsg hello = {};
     hello.magic = kLinkMagic;
     hello.n_slots = static_cast<uint32_t>(n_slots);
+    hello.quant_hint = static_cast<uint32_t>(quant_hint > 0 ? quant_hint : 0);
     hello.slot_bytes = l->slot_bytes;
     if (e == cudaSuccess) e = cudaIpcGetMemHandle(&hello.handle, l->local_block);
     if (e != cudaSuccess) {
@@ -1080,6 +1105,7 @@ int pe_link_open(int fd, int is_producer, size_t slot_payload_bytes, int n_slots
       return PE_ERR_CUDA;
     }
     l->n_slots = static_cast<int>(hello.n_slots);
+    l->quant_hint = static_cast<int>(hello.quant_hint);
     l->slot_bytes = hello.slot_bytes;
     const size_t block = kFlagsBytes + l->slot_bytes * l->n_slots;
     cudaError_t e = cudaMalloc(&l->local_block, block);
@@ -1106,7 +1132,7 @@ int pe_link_open(int fd, int is_producer, size_t slot_payload_bytes, int n_slots
 }
 
 // Both ends in this process (a one-rank pipeline's results path; tests): same kernels, same flags, no cudaIpc.
-int pe_link_open_local(size_t slot_payload_bytes, int n_slots, pe_link** out) {
+int pe_link_open_local(size_t slot_payload_bytes, int n_slots, int quant_hint, pe_link** out) {
   using namespace pe;
   PE_REQUIRE(out != nullptr && n_slots >= 2 && n_slots <= kLinkMaxSlots && slot_payload_bytes > 0,
              "pe_link_open_local: bad arguments");
@@ -1115,6 +1141,7 @@ int pe_link_open_local(size_t slot_payload_bytes, int n_slots, pe_link** out) {
   pe_link* l = new pe_link();
   l->kind = 1;
   l->is_tx = l->is_rx = true;
+  l->quant_hint = quant_hint;
   rc = alloc_common(l);
   if (rc != PE_OK) { free_link(l); return rc; }
   int sv[2];

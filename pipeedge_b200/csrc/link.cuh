@@ -97,6 +97,10 @@ struct pe_link {
   size_t quant_work_bytes = 0;
   unsigned long long timeout_ns = 0;
   int wire_f16 = 0;
+  int sync_mode = 0;               // PE_LINK_SYNC bit 0: flags polled with relaxed (volatile) loads; bit 1: one GPU-scope
+                                   // fence per CTA + one system-scope fence by the publishing CTA
+  int grid_cap = 0;                // PE_LINK_GRID_CAP: CTAs of the copy / decode kernels (0 = chosen per kernel)
+  int quant_hint = 0;              // bit-width the producer announced at open (0 = raw payloads)
 };
 
 namespace pe {

@@ -36,7 +36,7 @@ act8 = torch.randn(8, 197, 768, device=dev, generator=g)
 ids = torch.randint(0, 30522, (32, 128), device=dev)
 
 loop = ctypes.c_void_p()
-check(LIB.pe_link_open_local(hop.numel() * 4 + 4096, 4, ctypes.byref(loop)))
+check(LIB.pe_link_open_local(hop.numel() * 4 + 4096, 4, 8, ctypes.byref(loop)))
 dst = torch.empty_like(hop)
 dst8 = torch.empty_like(act8)
 stream = torch.cuda.current_stream().cuda_stream

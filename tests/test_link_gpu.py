@@ -27,7 +27,7 @@ class Loop:
     def __init__(self, lib, payload_bytes, slots=4):
         self.lib = lib
         self.h = ctypes.c_void_p()
-        lib.check(lib.LIB.pe_link_open_local(payload_bytes, slots, ctypes.byref(self.h)))
+        lib.check(lib.LIB.pe_link_open_local(payload_bytes, slots, 8, ctypes.byref(self.h)))
 
     def close(self):
         self.lib.LIB.pe_link_close(self.h)
