@@ -84,7 +84,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.QUERY}',
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '25'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
         except OSError:
@@ -466,8 +466,10 @@ def run_gpu(args, spec, ubatch, seq, qbit, metric, unit, workload):
             if rank == 0:
                 per_step = max(wall_w / warmup, 1e-4)
                 extra = int(min(2000, max(0.0, 0.3 - wall_w) / per_step))
-            run_phase(max(extra, 1), False)
+            # the clock sampler spans the second warm-up phase too: a 20-step timed phase lasts ~10 ms, less than one
+            # nvidia-smi sampling period, and both phases run the same load back to back
             with ClockSampler(local) as clocks:
+                run_phase(max(extra, 1), False)
                 _, tim = run_phase(steps, False)
             ms_rank = max(tim['compute_ms'], tim['results_ms'])
             ms = allmax(ms_rank)
