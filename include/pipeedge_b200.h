@@ -275,10 +275,14 @@ int pe_pipe_destroy(pe_pipe* pipe);
 void* pe_pipe_stream(pe_pipe* pipe);
 void* pe_pipe_copy_stream(pe_pipe* pipe);
 int pe_pipe_has_graph(pe_pipe* pipe, int ubatch, long long dim1);
-int pe_pipe_capture_begin(pe_pipe* pipe, int ubatch, long long dim1, void* dst0, void* dst1, size_t n0, size_t n1,
-                          size_t raw_bytes);
+/* Capture for buffer parity 0 (and, with an overlapped send, 1): begin enqueues the receive into dst0 / dst1, the caller
+ * then enqueues the stage's kernels on pe_pipe_stream(), end adds the send - inside the same graph (overlap == 0) or as
+ * a graph of its own on a second stream that overlaps the NEXT micro-batch's receive and first kernels (overlap != 0:
+ * the stage must write its output into a different buffer set per parity; micro-batch i uses parity i mod 2). */
+int pe_pipe_capture_begin(pe_pipe* pipe, int ubatch, long long dim1, int parity, void* dst0, void* dst1, size_t n0,
+                          size_t n1, size_t raw_bytes);
 int pe_pipe_capture_end(pe_pipe* pipe, const void* a0, const void* b0, size_t n0, const void* a1, const void* b1,
-                        size_t n1, int items, int bit, int clamp, int* kernels);
+                        size_t n1, int items, int bit, int clamp, int overlap, int* kernels);
 int pe_pipe_capture_abort(pe_pipe* pipe);
 int pe_pipe_invalidate(pe_pipe* pipe);
 int pe_pipe_submit(pe_pipe* pipe, const void* src, size_t bytes, int src_is_host, int ubatch, long long dim1);

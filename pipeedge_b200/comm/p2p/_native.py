@@ -46,6 +46,13 @@ def drain_barrier(seconds: float = 120.0) -> None:
         logger.exception("native pipeline: a rank did not reach the drain barrier")
 
 
+def overlap_send() -> bool:
+    """Whether a stage's send runs on its own stream and overlaps the next micro-batch (`PIPEEDGE_OVERLAP_SEND`, default
+    on): the stage then alternates between two output buffer sets and always materialises its output (no residual add
+    left to the send kernel)."""
+    return os.environ.get('PIPEEDGE_OVERLAP_SEND', '1') != '0'
+
+
 def hook_is_native(hook) -> bool:
     """Whether a module hook is represented by the native pipeline's kernels (quantisation encode / decode) or is a
     no-op there (device placement, disabled monitoring): marked by `_pe_native` (a bool or a callable)."""
@@ -186,34 +193,36 @@ class NativeStage:
                 check(LIB.pe_pipe_invalidate(self._pipe))   # the stage's workspace is about to be re-created
                 self.graph_kernels.clear()
             bit, clamp = self._quant()
+            overlap = overlap_send()
             with torch.cuda.stream(self._stream):
                 ins = self._inputs.get((ubatch, dim1))
                 if ins is None:     # zero-filled (valid token ids / finite activations for the eager run below)
                     ins = [torch.zeros(shape, dtype=dtype, device=torch.device('cuda', self._device))
                            for shape, dtype in shard.native_input_spec(ubatch, dim1)]
                     self._inputs[(ubatch, dim1)] = ins
-                # eager run on the same buffers first: sizes every persistent buffer and does all first-use work
-                # (module loads, function attributes, tensor-map driver entry points) outside the capture
-                shard.native_forward(ins)
-                self._stream.synchronize()
-                if self._is_data:
-                    raw = ins[0].numel() * ins[0].element_size()
-                    check(LIB.pe_pipe_capture_begin(self._pipe, ubatch, dim1, ins[0].data_ptr(), None, 0, 0, raw))
-                else:
-                    n0 = ins[0].numel() // ubatch
-                    n1 = ins[1].numel() // ubatch if len(ins) > 1 else 0
-                    check(LIB.pe_pipe_capture_begin(self._pipe, ubatch, dim1, ins[0].data_ptr(),
-                                                    ins[1].data_ptr() if len(ins) > 1 else None, n0, n1, 0))
-                try:
-                    parts = shard.native_forward(ins)
-                except BaseException:
-                    LIB.pe_pipe_capture_abort(self._pipe)
-                    raise
-                a0, b0, m0 = parts[0]
-                a1, b1, m1 = parts[1] if len(parts) > 1 else (None, None, 0)
                 kernels = ctypes.c_int(0)
-                check(LIB.pe_pipe_capture_end(self._pipe, a0, b0, m0, a1, b1, m1, ubatch, bit, clamp,
-                                              ctypes.byref(kernels)))
+                for parity in range(2 if overlap else 1):
+                    # eager run on the same buffers first: sizes every persistent buffer and does all first-use work
+                    # (module loads, function attributes, tensor-map driver entry points) outside the capture
+                    shard.native_forward(ins, parity, defer=not overlap)
+                    self._stream.synchronize()
+                    if self._is_data:
+                        raw = ins[0].numel() * ins[0].element_size()
+                        check(LIB.pe_pipe_capture_begin(self._pipe, ubatch, dim1, parity, ins[0].data_ptr(), None, 0, 0, raw))
+                    else:
+                        n0 = ins[0].numel() // ubatch
+                        n1 = ins[1].numel() // ubatch if len(ins) > 1 else 0
+                        check(LIB.pe_pipe_capture_begin(self._pipe, ubatch, dim1, parity, ins[0].data_ptr(),
+                                                        ins[1].data_ptr() if len(ins) > 1 else None, n0, n1, 0))
+                    try:
+                        parts = shard.native_forward(ins, parity, defer=not overlap)
+                    except BaseException:
+                        LIB.pe_pipe_capture_abort(self._pipe)
+                        raise
+                    a0, b0, m0 = parts[0]
+                    a1, b1, m1 = parts[1] if len(parts) > 1 else (None, None, 0)
+                    check(LIB.pe_pipe_capture_end(self._pipe, a0, b0, m0, a1, b1, m1, ubatch, bit, clamp,
+                                                  1 if overlap else 0, ctypes.byref(kernels)))
             self.graph_kernels[(ubatch, dim1)] = kernels.value
 
     # ------------------------------------------------------------------ data rank

@@ -33,11 +33,20 @@ struct pe_pipe {
   pe_link* in = nullptr;
   pe_link* out = nullptr;
   pe_link* res = nullptr;
-  cudaStream_t compute = nullptr, copy = nullptr, results = nullptr;
+  cudaStream_t compute = nullptr, copy = nullptr, results = nullptr, put = nullptr;
+  // Overlapped send (capture_end with overlap != 0): the stage writes its output into one of TWO buffer sets (parity =
+  // micro-batch index mod 2); the link's send kernel runs as its own graph on the `put` stream and overlaps the next
+  // micro-batch's receive / first kernels; events order main(i) -> put(i) -> main(i + 2).
   struct Graph {
-    cudaGraphExec_t exec = nullptr;
+    cudaGraphExec_t exec[2] = {nullptr, nullptr};       // get + stage kernels (+ put when not overlapped), per parity
+    cudaGraphExec_t exec_put[2] = {nullptr, nullptr};   // the send on its own stream (overlapped mode)
+    int n_par = 0;                                      // parities captured so far
+    int want_par = 1;                                   // 1 (send inside the main graph) or 2 (overlapped)
     int kernels = 0;
   };
+  cudaEvent_t ev_main_done[2] = {nullptr, nullptr}, ev_put_done[2] = {nullptr, nullptr};
+  bool put_pending[2] = {false, false};
+  int cap_parity = 0;
   std::map<std::pair<int, long long>, Graph> graphs;
   std::mutex graphs_mu;    // prepare() on the owner thread may insert while the stage thread looks a graph up
   bool capturing = false;
@@ -66,9 +75,18 @@ namespace pe {
 static bool find_graph(pe_pipe* p, int ubatch, long long dim1, pe_pipe::Graph* out) {
   std::lock_guard<std::mutex> lock(p->graphs_mu);
   auto it = p->graphs.find(std::make_pair(ubatch, dim1));
-  if (it == p->graphs.end()) return false;
+  if (it == p->graphs.end() || it->second.n_par < it->second.want_par) return false;   // every parity captured?
   if (out != nullptr) *out = it->second;
   return true;
+}
+
+static void destroy_graph(pe_pipe::Graph& g) {
+  for (int i = 0; i < 2; ++i) {
+    if (g.exec[i] != nullptr) cudaGraphExecDestroy(g.exec[i]);
+    if (g.exec_put[i] != nullptr) cudaGraphExecDestroy(g.exec_put[i]);
+    g.exec[i] = g.exec_put[i] = nullptr;
+  }
+  g.n_par = 0;
 }
 
 static int launch_graph(pe_pipe* p, int ubatch, long long dim1) {
@@ -83,9 +101,28 @@ static int launch_graph(pe_pipe* p, int ubatch, long long dim1) {
     p->timed_launches = 0;
     p->timed_kernels = 0;
   }
-  PE_CUDA(cudaGraphLaunch(g.exec, p->compute));
-  PE_CUDA(cudaEventRecord(p->ev_last, p->compute));
-  PE_CUDA(cudaEventRecord(p->window[w], p->compute));
+  if (g.want_par == 2) {
+    const int par = static_cast<int>(p->launched & 1);
+    if (p->put_pending[par]) PE_CUDA(cudaStreamWaitEvent(p->compute, p->ev_put_done[par], 0));   // its buffers are free again
+    PE_CUDA(cudaGraphLaunch(g.exec[par], p->compute));
+    PE_CUDA(cudaEventRecord(p->ev_main_done[par], p->compute));
+    PE_CUDA(cudaStreamWaitEvent(p->put, p->ev_main_done[par], 0));
+    PE_CUDA(cudaGraphLaunch(g.exec_put[par], p->put));
+    PE_CUDA(cudaEventRecord(p->ev_put_done[par], p->put));
+    p->put_pending[par] = true;
+    PE_CUDA(cudaEventRecord(p->ev_last, p->put));
+    PE_CUDA(cudaEventRecord(p->window[w], p->put));
+  } else {
+    // a previous overlapped micro-batch may still be sending out of the buffers this graph writes
+    for (int par = 0; par < 2; ++par)
+      if (p->put_pending[par]) {
+        PE_CUDA(cudaStreamWaitEvent(p->compute, p->ev_put_done[par], 0));
+        p->put_pending[par] = false;
+      }
+    PE_CUDA(cudaGraphLaunch(g.exec[0], p->compute));
+    PE_CUDA(cudaEventRecord(p->ev_last, p->compute));
+    PE_CUDA(cudaEventRecord(p->window[w], p->compute));
+  }
   ++p->launched;
   ++p->timed_launches;
   p->timed_kernels += static_cast<uint64_t>(g.kernels);
@@ -115,6 +152,11 @@ int pe_pipe_create(pe_link* in, pe_link* out, pe_link* res, pe_pipe** out_pipe) 
   cudaError_t e = cudaStreamCreateWithFlags(&p->compute, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->copy, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->results, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->put, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&p->ev_main_done[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_put_done[i], cudaEventDisableTiming);
+  }
   for (int i = 0; i < kPipeWindow && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&p->window[i], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreate(&p->ev_first);
   if (e == cudaSuccess) e = cudaEventCreate(&p->ev_last);
@@ -136,10 +178,15 @@ int pe_pipe_create(pe_link* in, pe_link* out, pe_link* res, pe_pipe** out_pipe) 
 int pe_pipe_destroy(pe_pipe* p) {
   if (p == nullptr) return PE_OK;
   if (p->compute != nullptr) cudaStreamSynchronize(p->compute);
+  if (p->put != nullptr) cudaStreamSynchronize(p->put);
   if (p->results != nullptr) cudaStreamSynchronize(p->results);
   if (p->copy != nullptr) cudaStreamSynchronize(p->copy);
-  for (auto& kv : p->graphs)
-    if (kv.second.exec != nullptr) cudaGraphExecDestroy(kv.second.exec);
+  for (auto& kv : p->graphs) pe::destroy_graph(kv.second);
+  for (int i = 0; i < 2; ++i) {
+    if (p->ev_main_done[i] != nullptr) cudaEventDestroy(p->ev_main_done[i]);
+    if (p->ev_put_done[i] != nullptr) cudaEventDestroy(p->ev_put_done[i]);
+  }
+  if (p->put != nullptr) cudaStreamDestroy(p->put);
   for (int i = 0; i < pe::kPipeWindow; ++i)
     if (p->window[i] != nullptr) cudaEventDestroy(p->window[i]);
   if (p->ev_first != nullptr) cudaEventDestroy(p->ev_first);
@@ -166,11 +213,14 @@ int pe_pipe_has_graph(pe_pipe* p, int ubatch, long long dim1) {
 // Start capturing the graph for micro-batches of `ubatch` items (`dim1`: sequence length, part of the key). The get
 // kernel is enqueued first: from a host-fed link `raw_bytes` bytes land in dst0; from a hop the payload's one or two
 // tensors ([ubatch, n0] / [ubatch, n1] f32 after decoding) land in dst0 / dst1.
-int pe_pipe_capture_begin(pe_pipe* p, int ubatch, long long dim1, void* dst0, void* dst1, size_t n0, size_t n1,
+int pe_pipe_capture_begin(pe_pipe* p, int ubatch, long long dim1, int parity, void* dst0, void* dst1, size_t n0, size_t n1,
                           size_t raw_bytes) {
   using namespace pe;
-  PE_REQUIRE(p != nullptr && !p->capturing && ubatch > 0, "pe_pipe_capture_begin: bad state / arguments");
+  PE_REQUIRE(p != nullptr && !p->capturing && ubatch > 0 && (parity == 0 || parity == 1),
+             "pe_pipe_capture_begin: bad state / arguments");
   PE_CUDA(cudaStreamSynchronize(p->compute));
+  PE_CUDA(cudaStreamSynchronize(p->put));
+  p->cap_parity = parity;
   PE_CUDA(cudaStreamBeginCapture(p->compute, cudaStreamCaptureModeRelaxed));
   p->capturing = true;
   p->cap_ubatch = ubatch;
@@ -193,41 +243,76 @@ int pe_pipe_capture_abort(pe_pipe* p) {
   return PE_OK;
 }
 
-// Finish the graph: enqueue the put of the stage's output (x_i = a_i + b_i when b_i != NULL; QuantPipe `bit` / `clamp`
-// as pe_link_put), end the capture, instantiate. Returns the number of kernels in the graph in *kernels.
-int pe_pipe_capture_end(pe_pipe* p, const void* a0, const void* b0, size_t n0, const void* a1, const void* b1, size_t n1,
-                        int items, int bit, int clamp, int* kernels) {
-  using namespace pe;
-  PE_REQUIRE(p != nullptr && p->capturing, "pe_pipe_capture_end: no capture in progress");
-  PutTensor t[2] = {{static_cast<const float*>(a0), static_cast<const float*>(b0), n0},
-                    {static_cast<const float*>(a1), static_cast<const float*>(b1), n1}};
-  int rc = link_put(p->out, t, a1 != nullptr ? 2 : 1, items, bit, clamp, p->compute);
-  if (rc != PE_OK) {
-    pe_pipe_capture_abort(p);
-    return rc;
-  }
+static int end_capture(cudaStream_t stream, cudaGraphExec_t* exec, const char* what) {
   cudaGraph_t graph = nullptr;
-  const cudaError_t end = cudaStreamEndCapture(p->compute, &graph);
-  p->capturing = false;
+  const cudaError_t end = cudaStreamEndCapture(stream, &graph);
   if (end != cudaSuccess || graph == nullptr) {
     if (graph != nullptr) cudaGraphDestroy(graph);
-    return check_cuda(end != cudaSuccess ? end : cudaErrorUnknown, "cudaStreamEndCapture (pipe)");
+    return pe::check_cuda(end != cudaSuccess ? end : cudaErrorUnknown, what);
   }
-  pe_pipe::Graph g;
-  const cudaError_t inst = cudaGraphInstantiate(&g.exec, graph, 0);
+  const cudaError_t inst = cudaGraphInstantiate(exec, graph, 0);
   cudaGraphDestroy(graph);
   PE_CUDA(inst);
-  PE_CUDA(cudaGraphUpload(g.exec, p->compute));   // the first replay must not pay for moving the graph to the device
-  PE_CUDA(cudaStreamSynchronize(p->compute));
-  g.kernels = static_cast<int>(launch_count_now() - p->cap_launch0);
+  PE_CUDA(cudaGraphUpload(*exec, stream));   // the first replay must not pay for moving the graph to the device
+  PE_CUDA(cudaStreamSynchronize(stream));
+  return PE_OK;
+}
+
+// Finish the capture started by pe_pipe_capture_begin for its parity: the put of the stage's output (x_i = a_i + b_i when
+// b_i != NULL; QuantPipe `bit` / `clamp` as pe_link_put) goes into the same graph (overlap == 0; parity must be 0) or
+// into a graph of its own on the send stream (overlap != 0: capture parity 0 AND 1, each over its own output buffers).
+// *kernels = kernels per micro-batch.
+int pe_pipe_capture_end(pe_pipe* p, const void* a0, const void* b0, size_t n0, const void* a1, const void* b1, size_t n1,
+                        int items, int bit, int clamp, int overlap, int* kernels) {
+  using namespace pe;
+  PE_REQUIRE(p != nullptr && p->capturing, "pe_pipe_capture_end: no capture in progress");
+  PE_REQUIRE(overlap != 0 || p->cap_parity == 0, "pe_pipe_capture_end: parity 1 exists only with an overlapped send");
+  PutTensor t[2] = {{static_cast<const float*>(a0), static_cast<const float*>(b0), n0},
+                    {static_cast<const float*>(a1), static_cast<const float*>(b1), n1}};
+  const int par = p->cap_parity;
+  cudaGraphExec_t exec_main = nullptr, exec_put = nullptr;
+  int rc;
+  if (overlap == 0) {
+    rc = link_put(p->out, t, a1 != nullptr ? 2 : 1, items, bit, clamp, p->compute);
+    if (rc != PE_OK) {
+      pe_pipe_capture_abort(p);
+      return rc;
+    }
+  }
+  p->capturing = false;
+  rc = end_capture(p->compute, &exec_main, "cudaStreamEndCapture (pipe)");
+  if (rc != PE_OK) return rc;
+  if (overlap != 0) {
+    PE_CUDA(cudaStreamBeginCapture(p->put, cudaStreamCaptureModeRelaxed));
+    rc = link_put(p->out, t, a1 != nullptr ? 2 : 1, items, bit, clamp, p->put);
+    if (rc != PE_OK) {
+      cudaGraph_t graph = nullptr;
+      cudaStreamEndCapture(p->put, &graph);
+      if (graph != nullptr) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      cudaGraphExecDestroy(exec_main);
+      return rc;
+    }
+    rc = end_capture(p->put, &exec_put, "cudaStreamEndCapture (pipe, send)");
+    if (rc != PE_OK) {
+      cudaGraphExecDestroy(exec_main);
+      return rc;
+    }
+  }
+  const int captured = static_cast<int>(launch_count_now() - p->cap_launch0);
+  int total = captured;
   {
     std::lock_guard<std::mutex> lock(p->graphs_mu);
-    auto key = std::make_pair(p->cap_ubatch, p->cap_dim1);
-    auto old = p->graphs.find(key);
-    if (old != p->graphs.end() && old->second.exec != nullptr) cudaGraphExecDestroy(old->second.exec);
-    p->graphs[key] = g;
+    pe_pipe::Graph& g = p->graphs[std::make_pair(p->cap_ubatch, p->cap_dim1)];
+    if (par == 0) destroy_graph(g);   // a fresh capture of this key starts with parity 0
+    g.want_par = overlap != 0 ? 2 : 1;
+    g.exec[par] = exec_main;
+    g.exec_put[par] = exec_put;
+    g.n_par = par + 1;
+    g.kernels = captured;
+    total = g.kernels;
   }
-  if (kernels != nullptr) *kernels = g.kernels;
+  if (kernels != nullptr) *kernels = total;
   return PE_OK;
 }
 
@@ -235,9 +320,9 @@ int pe_pipe_capture_end(pe_pipe* p, const void* a0, const void* b0, size_t n0, c
 int pe_pipe_invalidate(pe_pipe* p) {
   PE_REQUIRE(p != nullptr && !p->capturing, "pe_pipe_invalidate: bad state");
   PE_CUDA(cudaStreamSynchronize(p->compute));
+  PE_CUDA(cudaStreamSynchronize(p->put));
   std::lock_guard<std::mutex> lock(p->graphs_mu);
-  for (auto& kv : p->graphs)
-    if (kv.second.exec != nullptr) cudaGraphExecDestroy(kv.second.exec);
+  for (auto& kv : p->graphs) pe::destroy_graph(kv.second);
   p->graphs.clear();
   return PE_OK;
 }
@@ -281,6 +366,7 @@ int pe_pipe_run(pe_pipe* p, long long* need2) {
       if (r == 1 || p->pend[0] < 0) {
         link_ticket_send(p->out, -1, 0);
         PE_CUDA(cudaStreamSynchronize(p->compute));
+        PE_CUDA(cudaStreamSynchronize(p->put));
         const int rc = link_check(p->in);
         return rc != PE_OK ? rc : 1;
       }
@@ -335,6 +421,7 @@ int pe_pipe_sync(pe_pipe* p) {
   PE_REQUIRE(p != nullptr, "pe_pipe_sync: null pipe");
   PE_CUDA(cudaStreamSynchronize(p->copy));
   PE_CUDA(cudaStreamSynchronize(p->compute));
+  PE_CUDA(cudaStreamSynchronize(p->put));
   int rc = link_check(p->in);
   if (rc == PE_OK) rc = link_check(p->out);
   return rc;

@@ -30,7 +30,9 @@ class GpuTransformerShard(ModuleShard):
         super().__init__(config, shard_config)
         self.use_cuda_graph = False
         self.num_slots = 4
-        self._static = False       # native pipeline capture: single persistent buffers, eager launches, deferred add
+        self._static = False       # native pipeline capture: persistent buffers, eager launches
+        self._static_parity = 0    # ... which of the two buffer sets (overlapped send: micro-batch index mod 2)
+        self._static_defer = True  # ... leave a final residual add to the link's send kernel
         self._deferred = None      # (a, b) device addresses when the last static forward deferred its final add
         self._slot = 0
         self._slot_sent = {}       # ring slot -> CUDA event recorded once the hop has SENT what the slot held
@@ -107,7 +109,7 @@ class GpuTransformerShard(ModuleShard):
 
     def _ring(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
         """Persistent buffer `name` of the current slot (allocated on first use per shape)."""
-        key = (name, tuple(shape), dtype, 0 if self._static else self._slot)
+        key = (name, tuple(shape), dtype, ('static', self._static_parity) if self._static else self._slot)
         buf = self._rings.get(key)
         if buf is None:
             buf = torch.empty(tuple(shape), dtype=dtype, device=self.stage.device)
@@ -139,7 +141,7 @@ class GpuTransformerShard(ModuleShard):
         if self._static:
             # captured by the native pipeline: plain launches; a non-final stage that ends on a projection leaves its
             # last residual add to the link's send kernel
-            res = self.stage.forward(data, out=out, defer_add=not self.shard_config.is_last)
+            res = self.stage.forward(data, out=out, defer_add=self._static_defer and not self.shard_config.is_last)
             self._deferred = self.stage.deferred()
             return res
         if self.use_cuda_graph:
@@ -207,19 +209,24 @@ class GpuTransformerShard(ModuleShard):
     def native_needs_resize(self, ubatch: int, dim1: int) -> bool:
         return self.stage.needs_resize(ubatch, dim1 or self.stage.tokens)
 
-    def native_forward(self, inputs):
+    def native_forward(self, inputs, parity: int = 0, defer: bool = True):
         """One forward on persistent buffers for graph capture (no hooks, no allocation after the first call per
-        shape): returns [(a, b or None, elements per item)] device addresses of the output payload (a + b)."""
+        shape and parity): returns [(a, b or None, elements per item)] device addresses of the output payload (a + b).
+        `parity` picks one of two output buffer sets (a send that overlaps the next micro-batch reads set i mod 2 while
+        the stage writes the other); `defer` leaves a final residual add to the send kernel (needs the single set)."""
         inner = self._inner()
         prev = (self._static, inner._static)
         self._static = inner._static = True
+        self._static_parity = inner._static_parity = parity
+        self._static_defer = inner._static_defer = defer
         inner._deferred = None
         try:
             data = inputs[0] if len(inputs) == 1 else tuple(inputs)
             out = self.forward(data)
             outs = out if isinstance(out, tuple) else (out,)
             ubatch = inputs[0].shape[0]
-            self._native_keep = outs   # the graph writes into these buffers for as long as it lives
+            self._native_keep = getattr(self, '_native_keep', {})
+            self._native_keep[(tuple(inputs[0].shape), parity)] = outs   # the graphs write into these for as long as they live
             if inner._deferred is not None and len(outs) == 1:
                 a, b = inner._deferred
                 return [(a, b, outs[0].numel() // ubatch)]
