@@ -74,26 +74,51 @@ def flops_per_item(spec, seq: int) -> float:
 
 
 class ClockSampler:
-    """Samples nvidia-smi SM clocks and throttle reasons while the timed region runs."""
+    """Samples nvidia-smi SM clocks and throttle reasons while the timed region runs.
+
+    nvidia-smi needs up to a second to start on an 8-GPU box - longer than a 20-step timed phase - so the sampler is
+    started ahead of the warm-up (`wait_first`), every sample is time-stamped, and the summary uses the samples that fall
+    into the marked window (`mark_start` .. `mark_end`: the second warm-up phase + the timed phase, the same load back to
+    back), or the sample nearest to it."""
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, enabled: bool = True):
         self.index, self.proc, self.lines = index, None, []
+        self.t_start = self.t_end = None
+        self.enabled = enabled
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line))
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.QUERY}',
                                           '--format=csv,noheader,nounits', '-lms', '25'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+            threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
         return self
 
+    def wait_first(self, timeout: float = 8.0):
+        """Block until the first sample has arrived (nvidia-smi is up), at most `timeout` seconds."""
+        deadline = time.perf_counter() + timeout
+        while self.proc is not None and not self.lines and time.perf_counter() < deadline:
+            time.sleep(0.01)
+
+    def mark_start(self):
+        self.t_start = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
+
     def __exit__(self, *exc):
         if self.proc is not None:
-            time.sleep(0.15)
+            time.sleep(0.06)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=5)
@@ -101,22 +126,27 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self) -> dict:
-        sm, mx, reasons = [], 0, set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for line in self.lines:
+        rows = []
+        for stamp, line in list(self.lines):
             parts = [p.strip() for p in line.split(',')]
             if len(parts) < 6:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx = max(mx, float(parts[1]))
+                rows.append((stamp, float(parts[0]), float(parts[1]),
+                             [n for n, v in zip(names, parts[2:6]) if v.lower().startswith('active')]))
             except ValueError:
                 continue
-            for name, val in zip(names, parts[2:6]):
-                if val.lower().startswith('active'):
-                    reasons.add(name)
-        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': mx or None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+        window = rows
+        if self.t_start is not None and self.t_end is not None and rows:
+            window = [r for r in rows if self.t_start <= r[0] <= self.t_end + 0.05]
+            if not window:   # shorter than one sampling period: the sample nearest to the window
+                mid = 0.5 * (self.t_start + self.t_end)
+                window = [min(rows, key=lambda r: abs(r[0] - mid))]
+        sm = [r[1] for r in window]
+        reasons = sorted({n for r in window for n in r[3]})
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max((r[2] for r in window), default=None),
+                'reasons': reasons, 'samples': len(sm), 'samples_total': len(rows)}
 
 
 def load_peaks() -> dict:
@@ -459,6 +489,9 @@ def run_gpu(args, spec, ubatch, seq, qbit, metric, unit, workload):
                 barrier()
                 return wall, tim
 
+            sampler = ClockSampler(local, enabled=rank == 0)   # the line reports the data rank's GPU
+            sampler.__enter__()
+            sampler.wait_first()
             wall_w, _ = run_phase(warmup, False)
             # ... and keep going (untimed) until the GPU has been busy for ~0.3 s: W micro-batches are a few ms of
             # work, not enough for the clocks to leave their idle state
@@ -468,9 +501,12 @@ def run_gpu(args, spec, ubatch, seq, qbit, metric, unit, workload):
                 extra = int(min(2000, max(0.0, 0.3 - wall_w) / per_step))
             # the clock sampler spans the second warm-up phase too: a 20-step timed phase lasts ~10 ms, less than one
             # nvidia-smi sampling period, and both phases run the same load back to back
-            with ClockSampler(local) as clocks:
-                run_phase(max(extra, 1), False)
-                _, tim = run_phase(steps, False)
+            clocks = sampler
+            clocks.mark_start()
+            run_phase(max(extra, 1), False)
+            _, tim = run_phase(steps, False)
+            clocks.mark_end()
+            clocks.__exit__(None, None, None)
             ms_rank = max(tim['compute_ms'], tim['results_ms'])
             ms = allmax(ms_rank)
             kernels = allsum(float(tim['kernels'])) + steps     # + the data rank's results-get kernel per micro-batch

@@ -73,14 +73,25 @@ def _native_lib():
     return LIB if LIB.pe_hop_available() else None
 
 
+_NCCL_HOPS_OPENED = 0
+
+
+def nccl_hops_opened() -> int:
+    """How many per-hop NCCL communicators this process has created (the Python-thread path; the native pipeline creates
+    none). Entry points use it to decide whether the process may leave through the normal interpreter exit."""
+    return _NCCL_HOPS_OPENED
+
+
 class _NativeHop:
     """`pe_hop_*`: one C call per payload and side moves the device tensors over the hop's NCCL communicator."""
 
     def __init__(self, lib, sock: socket.socket, is_sender: bool):
+        global _NCCL_HOPS_OPENED   # pylint: disable=global-statement
         from ..._lib import check   # pylint: disable=import-outside-toplevel
         self._lib, self._check = lib, check
         self._handle = ctypes.c_void_p()
         check(lib.pe_hop_open(sock.fileno(), 1 if is_sender else 0, ctypes.byref(self._handle)))
+        _NCCL_HOPS_OPENED += 1
 
     def close(self) -> None:
         if self._handle:

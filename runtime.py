@@ -510,9 +510,11 @@ if __name__ == "__main__":
     console_hndlr.setLevel(logging.INFO)
     logging.getLogger().addHandler(console_hndlr)
     main()
-    if torch.cuda.is_available():
-        # everything is shut down; skip the CUDA / NCCL libraries' exit-time teardown, which can crash after a clean
-        # multi-rank run (see bench.py)
+    from pipeedge_b200.comm import p2p as _p2p
+    if torch.cuda.is_available() and _p2p.nccl_hops_opened():
+        # Python-thread path only: everything is shut down, but the exit-time teardown of the CUDA / NCCL libraries can
+        # crash after a clean multi-rank run with per-hop communicators. The native pipeline owns no communicator and
+        # leaves through the normal interpreter exit (destroy graphs / events -> links -> process group, in that order).
         logging.shutdown()
         sys.stdout.flush()
         sys.stderr.flush()
