@@ -46,6 +46,11 @@ for label, shape, bit, with_b in (('raw 8x197x768', (8, 197, 768), 0, False), ('
     LIB.pe_link_close(h)
 """
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if os.environ.get('PE_ONLY_DEFAULT'):     # the library's defaults only
+    print("library defaults (PE_LINK_SYNC=2, copies on half the SMs)", flush=True)
+    env = {k: v for k, v in os.environ.items() if k not in ('PE_LINK_SYNC', 'PE_LINK_GRID_CAP')}
+    subprocess.run([sys.executable, '-c', CHILD, root], env=env, check=False)
+    sys.exit(0)
 for sync in ('0', '1', '2', '3'):
     for cap in ('0', '74', '37'):
         print(f"PE_LINK_SYNC={sync} PE_LINK_GRID_CAP={cap}", flush=True)
