@@ -214,7 +214,20 @@ def cpu_forward_timer(spec, ubatch: int, seq: int):
 def cpu_sample(spec, ubatch: int, seq: int, unit: str, max_steps: int, budget_s: float) -> dict:
     """Time the CPU port on a bounded sample; the same routine serves `cpu_baseline` and `--impl reference`."""
     fwd, cores, cal = cpu_forward_timer(spec, ubatch, seq)
-    fwd()
+    # Warm-up until the per-forward time has settled: the first forwards of a process run ~2x slower than its steady state
+    # (the allocator still maps and unmaps the 10-100 MB temporaries of every layer; r02g: 0.31 s vs 0.14 s per
+    # micro-batch), which is why a 20-step arm and a 64-step arm of the same code disagreed by 2x.
+    t_w = time.perf_counter()
+    warm, last = 0, float('inf')
+    while warm < 40 and time.perf_counter() - t_w < 12.0:
+        t1 = time.perf_counter()
+        fwd()
+        dt1 = time.perf_counter() - t1
+        warm += 1
+        if warm >= 5 and dt1 > 0.93 * last:     # no longer getting faster
+            break
+        last = min(last, dt1)
+    cal['warmup_forwards'] = warm
     t0 = time.perf_counter()
     n = 0
     while n < 2 or (n < max_steps and time.perf_counter() - t0 < budget_s):

@@ -197,6 +197,44 @@ def golden_adaptive():
     print('adaptive done')
 
 
+def golden_sched():
+    """The reference's `parse_yaml_sched` (`runtime.py:260-288`; the script itself cannot be imported here, so the
+    function is extracted from its source) on scheduler-format YAML -> tests/golden/sched.json."""
+    import ast    # pylint: disable=import-outside-toplevel
+    import json   # pylint: disable=import-outside-toplevel
+    import logging   # pylint: disable=import-outside-toplevel
+    import yaml   # pylint: disable=import-outside-toplevel
+    with open('/root/reference/runtime.py', encoding='utf8') as f:
+        tree = ast.parse(f.read())
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == 'parse_yaml_sched')
+    from typing import List, Optional, Tuple   # pylint: disable=import-outside-toplevel
+    scope = {'List': List, 'Optional': Optional, 'Tuple': Tuple, 'logger': logging.getLogger('ref')}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), 'ref_runtime', 'exec'), scope)   # pylint: disable=exec-used
+    ref = scope['parse_yaml_sched']
+    cases = [
+        ("- mb-a: [1, 24]\n- mb-b: [25, 48]\n", ['mb-a', 'mb-b']),
+        ("- mb-b: [1, 10]\n- mb-a: [11, 48]\n", ['mb-a', 'mb-b']),
+        ("- '1': [1, 6]\n- '0': [7, 30]\n- '2': [31, 48]\n", None),
+        ("- 3: [1, 96]\n", None),
+        ("- gpu0: [1, 6]\n- gpu1: [7, 12]\n- gpu2: [13, 18]\n- gpu3: [19, 24]\n- gpu4: [25, 30]\n- gpu5: [31, 36]\n"
+         "- gpu6: [37, 42]\n- gpu7: [43, 48]\n", [f'gpu{i}' for i in range(8)]),
+        ("- nosuch: [1, 48]\n", ['mb-a']),
+        ("- notarank: [1, 48]\n", None),
+        ("[]\n", None),
+    ]
+    out = []
+    for text, hosts in cases:
+        sched = yaml.safe_load(text)
+        try:
+            layers, ranks = ref(sched, hosts)
+            out.append({'yaml': text, 'hosts': hosts, 'layers': [list(l) for l in layers], 'ranks': ranks})
+        except (ValueError, RuntimeError) as exc:
+            out.append({'yaml': text, 'hosts': hosts, 'error': type(exc).__name__})
+    with open(os.path.join(OUT, 'sched.json'), 'w', encoding='utf8') as f:
+        json.dump(out, f, indent=1)
+    print('sched done')
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -207,10 +245,14 @@ def main():
         for name in sys.argv[2:]:
             golden_tiny(name)
         return
+    if sys.argv[1:] == ['sched']:
+        golden_sched()
+        return
     if sys.argv[1:] == ['vit-large']:
         golden_full('google/vit-large-patch16-224', 2, (24, 48, 72, 96))
         return
     golden_adaptive()
+    golden_sched()
     golden_quant()
     for name in ('test/vit-tiny', 'test/deit-tiny', 'test/bert-tiny', 'test/vit-huge-tiny'):
         golden_tiny(name)

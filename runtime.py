@@ -8,8 +8,9 @@ activations stay in HBM, the hop is NCCL on a side stream, and the QuantPipe hoo
 kernels (bit-identical codes). The adaptive QuantPipe policies (`ADAPTIVE_QUANT=HEURISTIC|HEURISTIC2|CONTROLLER`
 with `SEND_CONSTRAINT` items/s and `WINDOW_SIZE`, `runtime.py:121-216`) are carried over; they read the hop's
 DEVICE-side transfer time (CUDA events around the NCCL sends) through `monitoring.py`'s window statistics.
-What is NOT carried over (out of scope): the RPC backend (`-c rpc`), `sched-pipeline`
-automated scheduling (`-H/-sm/-sdt/-sd`), energy monitoring, and the dataset loaders that need the network; inputs are the reference's synthetic fallback (`runtime.py:386-400`)
+Scheduler-generated partitions are ingested in the scheduler's own YAML format (`parse_yaml_sched`, `-H`, `--sched-file`, or
+the reference's `sched-pipeline` binary when it is on PATH with `-sm/-sdt/-sd`). What is NOT carried over (out of scope,
+SURVEY.md section 2): the RPC backend (`-c rpc`), the `sched-pipeline` planner itself, energy monitoring, and the dataset loaders that need the network; inputs are the reference's synthetic fallback (`runtime.py:386-400`)
 generated locally, weights come from `-M` (an npz in the reference layout) or are synthesised.
 """
 import argparse
@@ -294,8 +295,60 @@ def handle_results(tensors: torch.Tensor) -> None:
     results_counter.add(n_items)
 
 
+def parse_yaml_sched(sched: List[dict], hosts: Optional[List[str]]) -> Tuple[List[Tuple[int, int]], List[int]]:
+    """Parse the scheduler's YAML (`sched-pipeline` prints a list of single-entry maps `host: [layer_start, layer_end]`)
+    into `stage_layers` and `stage_ranks` (`runtime.py:260-288`): a host is looked up in `hosts` (its index is the rank)
+    or, without a hosts list, is the rank itself."""
+    assert isinstance(sched, list)
+    if len(sched) == 0:
+        raise RuntimeError("No viable schedule found")
+    stage_layers, stage_ranks = [], []
+    for stage in sched:
+        assert len(stage) == 1          # one mapping per stage
+        for host, layers in stage.items():
+            assert len(layers) == 2
+            stage_layers.append((int(layers[0]), int(layers[1])))
+            if hosts:
+                try:
+                    stage_ranks.append(hosts.index(host))
+                except ValueError:
+                    logger.error("Scheduling: host not found in hosts list: %s", host)
+                    raise
+            else:
+                try:
+                    stage_ranks.append(int(host))
+                except ValueError:
+                    logger.error("Scheduling: 'hosts' not specified, failed to parse as rank: %s", host)
+                    raise
+    return stage_layers, stage_ranks
+
+
+def load_yaml_sched(model_name: str, microbatch_size: int, sched_file: Optional[str], s_models_file: Optional[str],
+                    s_dev_types_file: Optional[str], s_dev_file: Optional[str]) -> List[dict]:
+    """The scheduler's output: read from `sched_file` (what `sched-pipeline` printed), or produced now by the
+    reference's `sched-pipeline` binary if it is on PATH (same arguments as `sched/scheduler.py:24-70`; the
+    scheduler itself is CPU planning code outside this build's scope and is not rebuilt here)."""
+    import subprocess   # pylint: disable=import-outside-toplevel
+    import yaml         # pylint: disable=import-outside-toplevel
+    if sched_file:
+        with open(sched_file, encoding='utf-8') as fh:
+            return yaml.safe_load(fh)
+    args = ['sched-pipeline', '-i', '2', '-o', '2', '-b', str(microbatch_size), '-d', 'torch.float32', '-m', model_name]
+    for flag, val in (('-M', s_models_file), ('-T', s_dev_types_file), ('-D', s_dev_file)):
+        if val:
+            args += [flag, val]
+    try:
+        proc = subprocess.run(args, capture_output=True, check=True)
+    except FileNotFoundError as exc:
+        raise RuntimeError("Automated scheduling needs the reference's `sched-pipeline` on PATH (not built here): "
+                           "pass its output with --sched-file, or a partition with -pt") from exc
+    return yaml.safe_load(proc.stdout)
+
+
 def get_pipeline_sched(world_size: int, partition: Optional[List[Tuple[int, int]]], quant: Optional[List[int]],
-                       rank_order: Optional[List[int]], model_name: str) \
+                       rank_order: Optional[List[int]], model_name: str, hosts: Optional[List[str]] = None,
+                       microbatch_size: int = 8, sched_file: Optional[str] = None, s_models_file: Optional[str] = None,
+                       s_dev_types_file: Optional[str] = None, s_dev_file: Optional[str] = None) \
         -> Tuple[List[Tuple[int, int]], List[int], List[int]]:
     """Get the pipeline schedule: `stage_layers`, `stage_quant`, `stage_ranks` (`runtime.py:291-355`)."""
     if partition:
@@ -311,7 +364,12 @@ def get_pipeline_sched(world_size: int, partition: Optional[List[Tuple[int, int]
         stage_quant = [0]
         stage_ranks = [0]
     else:
-        raise RuntimeError("Automated scheduling (sched-pipeline) is outside this build's scope: pass -pt")
+        # the scheduler's YAML (`runtime.py:334-351`): hosts must cover the world, no quantization for automated schedules
+        if hosts and len(hosts) != world_size:
+            raise RuntimeError("Specified hosts count != world size")
+        sched = load_yaml_sched(model_name, microbatch_size, sched_file, s_models_file, s_dev_types_file, s_dev_file)
+        stage_layers, stage_ranks = parse_yaml_sched(sched, hosts)
+        stage_quant = [0] * len(stage_layers)
     logger.info("Scheduling: stage-to-layer mapping: %s", stage_layers)
     logger.info("Scheduling: stage output quantization: %s", stage_quant)
     logger.info("Scheduling: stage-to-rank mapping: %s", stage_ranks)
@@ -353,7 +411,8 @@ def handle_cmd(cmd: int, tensors: Tuple[torch.Tensor, ...]) -> None:
 
 def run_pipeline_p2p(world_size: int, rank: int, model_name: str, model_file: Optional[str], batch_size: int,
                      ubatch_size: int, partition: Optional[List[Tuple[int, int]]], quant: Optional[List[int]],
-                     rank_order: Optional[List[int]], data_rank: int) -> float:
+                     rank_order: Optional[List[int]], data_rank: int, hosts: Optional[List[str]] = None,
+                     sched_args: Optional[dict] = None) -> float:
     """Run the pipeline using P2P communication (`runtime.py:418-511`); returns throughput on the data rank."""
     global _device_iters   # pylint: disable=global-statement
     throughput = 0.0
@@ -367,7 +426,8 @@ def run_pipeline_p2p(world_size: int, rank: int, model_name: str, model_file: Op
     with DistP2pContext(('gloo',), {'world_size': world_size, 'rank': rank}, handle_cmd) as dist_ctx:
         if rank == 0:
             stage_layers, stage_quant, stage_ranks = get_pipeline_sched(world_size, partition, quant, rank_order,
-                                                                        model_name)
+                                                                        model_name, hosts=hosts,
+                                                                        microbatch_size=ubatch_size, **(sched_args or {}))
             dist_ctx.cmd_broadcast(CMD_SCHED, (torch.tensor(stage_layers), torch.tensor(stage_quant),
                                                torch.tensor(stage_ranks), torch.tensor(data_rank)))
         else:
@@ -478,6 +538,14 @@ def main() -> None:
                         help="comma-delimited list of quantization bits to use after each stage")
     usched.add_argument("-r", "--rank-order", type=str, default=None,
                         help="comma-delimited list of ranks in desired stage order; default: natural rank order")
+    parser.add_argument("-H", "--hosts", type=str,
+                        help="comma-delimited list of hosts in rank order; required for automated scheduling")
+    asched = parser.add_argument_group('Automated scheduling')
+    asched.add_argument("--sched-file", type=str,
+                        help="YAML printed by the reference's sched-pipeline (list of `host: [start, end]` maps)")
+    asched.add_argument("-sm", "--sched-models-file", default=None, type=str, help="models YAML file for sched-pipeline")
+    asched.add_argument("-sdt", "--sched-dev-types-file", default=None, type=str, help="device types YAML file")
+    asched.add_argument("-sd", "--sched-dev-file", default=None, type=str, help="devices YAML file")
     usched.add_argument("-D", "--data-rank", type=int, default=0,
                         help="rank where inputs are loaded and outputs are processed - must be "
                              "the same as stage=0 or not in the stage pipeline")
@@ -498,8 +566,11 @@ def main() -> None:
         device = f"cuda:{args.rank % max(1, torch.cuda.device_count())}"
     init_env(device, args.addr, args.port, args.socket_ifname if args.socket_ifname != 'lo0' else '')
     logger.info("Device: %s", devices.DEVICE)
+    hosts = args.hosts.split(',') if args.hosts else None
     run_pipeline_p2p(args.worldsize, args.rank, args.model_name, args.model_file, args.batch_size,
-                     args.ubatch_size, partition, quant, rank_order, args.data_rank)
+                     args.ubatch_size, partition, quant, rank_order, args.data_rank, hosts=hosts,
+                     sched_args={'sched_file': args.sched_file, 's_models_file': args.sched_models_file,
+                                 's_dev_types_file': args.sched_dev_types_file, 's_dev_file': args.sched_dev_file})
     logger.info("Total program execution time = %f", time.time() - tik)
 
 

@@ -189,3 +189,32 @@ def test_gemm_tile_plan_invariants():
         assert 2 <= p['stages'] <= 8 and (p['stages'] * stage_bytes <= budget or p['stages'] == 2)
     with pytest.raises(_lib.PipeEdgeB200Error):
         _gemm_plan(0, 8, 8, _lib.PE_EPI_F32)
+
+
+def test_parse_yaml_sched_matches_the_reference(tmp_path):
+    """`runtime.parse_yaml_sched` / `get_pipeline_sched` on the scheduler's YAML vs what the reference's own function
+    returned for the same documents (`tests/golden/sched.json`, made by `oracle/make_goldens.py sched`)."""
+    import json
+    import yaml
+    import runtime as rt
+    with open(os.path.join(ROOT, 'tests', 'golden', 'sched.json'), encoding='utf-8') as fh:
+        cases = json.load(fh)
+    assert len(cases) >= 8
+    for case in cases:
+        sched = yaml.safe_load(case['yaml'])
+        if 'error' in case:
+            with pytest.raises((ValueError, RuntimeError)) as info:
+                rt.parse_yaml_sched(sched, case['hosts'])
+            assert type(info.value).__name__ == case['error']
+        else:
+            layers, ranks = rt.parse_yaml_sched(sched, case['hosts'])
+            assert [list(l) for l in layers] == case['layers'] and ranks == case['ranks']
+    # through get_pipeline_sched with a schedule file, as `runtime.py RANK 8 -H gpu0,...,gpu7 --sched-file f` would
+    eight = next(c for c in cases if c.get('hosts') and len(c['hosts']) == 8)
+    path = tmp_path / 'sched.yml'
+    path.write_text(eight['yaml'])
+    layers, quant, ranks = rt.get_pipeline_sched(8, None, None, None, 'google/vit-base-patch16-224', hosts=eight['hosts'],
+                                                 sched_file=str(path))
+    assert [list(l) for l in layers] == eight['layers'] and ranks == eight['ranks'] and quant == [0] * 8
+    with pytest.raises(RuntimeError, match="hosts count"):
+        rt.get_pipeline_sched(4, None, None, None, 'google/vit-base-patch16-224', hosts=eight['hosts'], sched_file=str(path))
