@@ -179,6 +179,25 @@ def usable_cores() -> int:
     return cores
 
 
+def cpu_arm_process_state() -> str:
+    """Put the process into the state in which the CPU port runs FASTEST on the B200 hosts, in both CPU arms.
+
+    Measured (scripts/cpu_arm_trajectory.py, r02h, 2 x Xeon 8562Y+, 16-CPU quota, 16 threads): a fresh process runs one
+    ViT-B micro-batch in 0.296 s, forward after forward; the same code in a process that has created a CUDA context and one
+    pinned allocation first runs it in 0.142 s. That - not thread-count noise alone - is why round 1's reference arm (a
+    fresh process) and the GPU arm's `cpu_baseline` (a process with a context) disagreed by 2-3x. Confining the process
+    to one NUMA node did not reproduce the fast regime. The CPU arm gets the benefit of the doubt: when a CUDA device is
+    present the arm creates a context before it allocates anything, so both arms report the faster regime."""
+    if torch.cuda.is_available():
+        torch.cuda.init()
+        keep = torch.empty(1 << 20).pin_memory()
+        torch.zeros(8, device='cuda')
+        torch.cuda.synchronize()
+        cpu_arm_process_state.keep = keep
+        return 'cuda context + pinned allocation created first'
+    return 'no CUDA device: fresh process'
+
+
 def cpu_forward_timer(spec, ubatch: int, seq: int):
     """Returns (callable running one micro-batch through the whole model on the CPU, threads used, calibration log).
 
@@ -186,6 +205,7 @@ def cpu_forward_timer(spec, ubatch: int, seq: int):
     thread count is calibrated - median of 3 repetitions per candidate of the FULL model (of its first two blocks when
     a full forward takes more than 0.6 s), candidates {8, 16, 32, 64, 96, all usable}."""
     from oracle import shards as osh   # the one place bench.py may execute oracle/ (as the timed CPU baseline)
+    state = cpu_arm_process_state()
     weights = synth_weights(spec, seed=0)
     model = osh.PreparedShard(spec, weights, 1, spec.layers)
     x = synth_input(spec, ubatch, seed=1, seq_len=seq or 128)
@@ -207,7 +227,8 @@ def cpu_forward_timer(spec, ubatch: int, seq: int):
         log[n] = statistics.median(reps)
     best = min(log, key=log.get)
     torch.set_num_threads(best)
-    return (lambda: model.forward(x)), best, {'host_cores': limit, 'probe': 'full model' if probe is model else '2 blocks',
+    return (lambda: model.forward(x)), best, {'host_cores': limit, 'process_state': state,
+                                              'probe': 'full model' if probe is model else '2 blocks',
                                               'median_s_by_threads': {str(k): round(v, 4) for k, v in log.items()}}
 
 
