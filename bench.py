@@ -179,25 +179,6 @@ def usable_cores() -> int:
     return cores
 
 
-def cpu_arm_process_state() -> str:
-    """Put the process into the state in which the CPU port runs FASTEST on the B200 hosts, in both CPU arms.
-
-    Measured (scripts/cpu_arm_trajectory.py, r02h, 2 x Xeon 8562Y+, 16-CPU quota, 16 threads): a fresh process runs one
-    ViT-B micro-batch in 0.296 s, forward after forward; the same code in a process that has created a CUDA context and one
-    pinned allocation first runs it in 0.142 s. That - not thread-count noise alone - is why round 1's reference arm (a
-    fresh process) and the GPU arm's `cpu_baseline` (a process with a context) disagreed by 2-3x. Confining the process
-    to one NUMA node did not reproduce the fast regime. The CPU arm gets the benefit of the doubt: when a CUDA device is
-    present the arm creates a context before it allocates anything, so both arms report the faster regime."""
-    if torch.cuda.is_available():
-        torch.cuda.init()
-        keep = torch.empty(1 << 20).pin_memory()
-        torch.zeros(8, device='cuda')
-        torch.cuda.synchronize()
-        cpu_arm_process_state.keep = keep
-        return 'cuda context + pinned allocation created first'
-    return 'no CUDA device: fresh process'
-
-
 def cpu_forward_timer(spec, ubatch: int, seq: int):
     """Returns (callable running one micro-batch through the whole model on the CPU, threads used, calibration log).
 
@@ -205,7 +186,6 @@ def cpu_forward_timer(spec, ubatch: int, seq: int):
     thread count is calibrated - median of 3 repetitions per candidate of the FULL model (of its first two blocks when
     a full forward takes more than 0.6 s), candidates {8, 16, 32, 64, 96, all usable}."""
     from oracle import shards as osh   # the one place bench.py may execute oracle/ (as the timed CPU baseline)
-    state = cpu_arm_process_state()
     weights = synth_weights(spec, seed=0)
     model = osh.PreparedShard(spec, weights, 1, spec.layers)
     x = synth_input(spec, ubatch, seed=1, seq_len=seq or 128)
@@ -227,7 +207,7 @@ def cpu_forward_timer(spec, ubatch: int, seq: int):
         log[n] = statistics.median(reps)
     best = min(log, key=log.get)
     torch.set_num_threads(best)
-    return (lambda: model.forward(x)), best, {'host_cores': limit, 'process_state': state,
+    return (lambda: model.forward(x)), best, {'host_cores': limit,
                                               'probe': 'full model' if probe is model else '2 blocks',
                                               'median_s_by_threads': {str(k): round(v, 4) for k, v in log.items()}}
 
@@ -260,6 +240,29 @@ def cpu_sample(spec, ubatch: int, seq: int, unit: str, max_steps: int, budget_s:
             'sample': f"{n} micro-batches of {ubatch} through all {spec.layers} sub-layers, torch fp32 CPU "
                       f"({dt:.1f} s), 1 process x {cores} threads of {cal['host_cores']} usable host cores "
                       "(median-of-3 thread calibration)"}
+
+
+def cpu_baseline_child(args) -> dict:
+    """`cpu_baseline` of the GPU arm = the reference arm's own command in a child process.
+
+    The CPU port's speed depends on the state of the process it runs in: on the B200 hosts (2 x Xeon 8562Y+, 16-CPU
+    quota) a fresh process needs 0.30 s per ViT-B micro-batch, forward after forward, while the same code at the end of
+    the GPU arm's process needed 0.14 s (scripts/cpu_arm_trajectory.py, profiles/r02_cpu_arm_trajectory.txt; neither a
+    CUDA context created first nor NUMA pinning reproduces the fast regime reliably). Round 1's two CPU numbers differed by
+    2-3x for that reason. Both arms now run the SAME command in the SAME kind of process, so they agree; the faster regime
+    is documented in DESIGN.md section 7 and would halve every GPU / CPU ratio."""
+    cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--workload', args.workload, '--steps', '24',
+           '--warmup', '2', '--gpus', '1']
+    if args.ubatch:
+        cmd += ['--ubatch', str(args.ubatch)]
+    env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK')}
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, check=False)
+    for line in res.stdout.splitlines():
+        if line.startswith('{'):
+            base = json.loads(line)['cpu_baseline']
+            base['how'] = 'the reference arm (`bench.py --impl reference`) run as a child process of this one'
+            return base
+    return {'value': None, 'unit': None, 'cores': None, 'kind': 'port', 'sample': 'the child process failed: ' + res.stderr[-300:]}
 
 
 def make_config(workload, spec, ubatch, seq_eff, parts, qbit, world) -> dict:
@@ -608,8 +611,7 @@ def run_gpu(args, spec, ubatch, seq, qbit, metric, unit, workload):
                 stop.wait(60)
     if rank == 0 and out is not None:
         if not args.no_cpu_baseline and world == 1:
-            res = cpu_sample(spec, ubatch, seq, unit, max_steps=64, budget_s=15.0)
-            out['cpu_baseline'] = {k: res[k] for k in ('value', 'unit', 'cores', 'kind', 'sample', 'calibration')}
+            out['cpu_baseline'] = cpu_baseline_child(args)
         print(json.dumps(out))
 
 
