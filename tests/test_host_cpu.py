@@ -34,6 +34,15 @@ def test_no_gpu_means_loud_failure_not_fallback():
     from pipeedge_b200 import _lib
     rc = _lib.LIB.pe_layernorm(None, None, None, 1e-12, None, None, 1, 4, None)
     assert rc == -3 and b'no CUDA device' in _lib.LIB.pe_last_error()
+    import ctypes
+    handle = ctypes.c_void_p()
+    for rc in (_lib.LIB.pe_link_open_local(1 << 20, 4, 0, ctypes.byref(handle)),
+               _lib.LIB.pe_link_open_host(1 << 20, 4, ctypes.byref(handle)),
+               _lib.LIB.pe_linear_residual_layernorm(None, None, None, None, None, None, 1e-12, None, 0, None, 1, 768, 768, 1,
+                                                     None)):
+        assert rc < 0, "link / fused kernels must refuse to run without an sm_100 device"
+    assert _lib.LIB.pe_linear_ln_cluster(768) == 8 and _lib.LIB.pe_linear_ln_cluster(1024) == 8
+    assert _lib.LIB.pe_linear_ln_cluster(128) == 4 and _lib.LIB.pe_linear_ln_cluster(160) == 0      # host-only planning
     from pipeedge_b200.models.transformers._stage import EncoderStage
     from pipeedge_b200.synth import MODEL_SPECS, hf_config, synth_weights
     spec = MODEL_SPECS['test/vit-tiny']
