@@ -91,6 +91,7 @@ class NativeStage:
         self.exception: Optional[BaseException] = None
         self.graph_kernels = {}               # (ubatch, dim1) -> kernels per micro-batch
         self._result_shape = None
+        self._captured_bit = None             # the QuantPipe bit-width the captured graphs send with
         self._stream = None
         self._copy_stream = None
 
@@ -176,6 +177,14 @@ class NativeStage:
         bit = int(shard.quant_bit)
         return bit, (_lib.PE_CLAMP_AUTO if bit > 0 else _lib.PE_CLAMP_NONE)
 
+    def invalidate(self) -> None:
+        """Forget the captured graphs (they bake in the shard's `quant_bit` and buffer addresses): the next payload of
+        each shape captures again. For callers that change a stage's bit-width between micro-batches by hand - the
+        adaptive policies do it from forward hooks, which select the Python-thread path in the first place."""
+        with self._capture_lock:
+            check(LIB.pe_pipe_invalidate(self._pipe))
+            self.graph_kernels.clear()
+
     def prepare(self, ubatch: int, dim1: int = 0) -> None:
         """Capture the graph for micro-batches of `ubatch` items (`dim1`: sequence length for BERT) ahead of the first
         payload, so that micro-batch 1 is already a replay."""
@@ -224,6 +233,7 @@ class NativeStage:
                     check(LIB.pe_pipe_capture_end(self._pipe, a0, b0, m0, a1, b1, m1, ubatch, bit, clamp,
                                                   1 if overlap else 0, ctypes.byref(kernels)))
             self.graph_kernels[(ubatch, dim1)] = kernels.value
+            self._captured_bit = bit
 
     # ------------------------------------------------------------------ data rank
     def enqueue(self, tensor: torch.Tensor) -> None:
@@ -232,6 +242,8 @@ class NativeStage:
         shape, dtype = self._shard.native_input_spec(tensor.shape[0], 0)[0]
         dim1 = int(tensor.shape[1]) if len(shape) == 2 else 0          # BERT: the sequence length is the payload's
         ubatch = int(tensor.shape[0])
+        if self._captured_bit is not None and self._quant()[0] != self._captured_bit:
+            self.invalidate()     # the data rank's own bit-width was changed since its graphs were captured
         if not LIB.pe_pipe_has_graph(self._pipe, ubatch, dim1):
             self._capture(ubatch, dim1)
         if tensor.dtype != dtype or not tensor.is_contiguous():
