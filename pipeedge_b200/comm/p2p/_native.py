@@ -92,6 +92,7 @@ class NativeStage:
         self.graph_kernels = {}               # (ubatch, dim1) -> kernels per micro-batch
         self._result_shape = None
         self._captured_bit = None             # the QuantPipe bit-width the captured graphs send with
+        self._quant_key, self._quant_val = None, 0
         self._stream = None
         self._copy_stream = None
 
@@ -171,10 +172,17 @@ class NativeStage:
 
     # ------------------------------------------------------------------ graph capture
     def _quant(self):
+        """(bit-width, clamp mode) this stage sends with: the shard's `quant_bit` buffer (`runtime.py:79`), 0 on the
+        last stage. The tensor is converted once per object / in-place version, never per micro-batch (a CUDA-resident
+        buffer would cost a device synchronisation each time)."""
         shard = self._shard
         if shard.shard_config.is_last or not hasattr(shard, 'quant_bit'):
             return 0, _lib.PE_CLAMP_NONE
-        bit = int(shard.quant_bit)
+        qb = shard.quant_bit
+        key = (id(qb), getattr(qb, '_version', 0))
+        if key != self._quant_key:
+            self._quant_key, self._quant_val = key, int(qb)
+        bit = self._quant_val
         return bit, (_lib.PE_CLAMP_AUTO if bit > 0 else _lib.PE_CLAMP_NONE)
 
     def invalidate(self) -> None:
